@@ -1,0 +1,249 @@
+/*
+ * pcdarts_sm100.h — C ABI of libpcdarts_sm100.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for ONE hot path of aahamed/LCT-VQA: forward + backward of the PC-DARTS search
+ * network (MixedOp / Cell / Network).  Every entry point replaces the ATen/cuDNN dispatch sequence
+ * of one reference module's forward (and the autograd backward of that sequence); the reference
+ * interface each one stands in for is cited as path:line under the upstream repo.
+ *
+ * Conventions (all entry points)
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - tensors are fp32, logical NCHW, W contiguous, channel stride = H*W; the batch stride is
+ *     explicit where a tensor may be a channel slice of a larger one.
+ *   - the library never allocates, frees, retains pointers or synchronises; every workspace is
+ *     caller-owned; all work is enqueued on `stream` (CUDA-graph capturable).
+ *   - return value: 0 on success, a negative pcd_status otherwise; never throws, never exits.
+ *   - re-entrant; no global mutable state except idempotent cudaFuncSetAttribute calls.
+ *   - BatchNorm is training-mode only (batch statistics, running stats updated in place,
+ *     unbiased variance, num_batches_tracked += 1), eps/momentum as given.
+ */
+#ifndef PCDARTS_SM100_H
+#define PCDARTS_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCD_VERSION 100          /* 0.1.0 */
+#define PCD_NUM_PRIMITIVES 8     /* genotypes.py:5-14 */
+#define PCD_MAX_STEPS 4
+#define PCD_MAX_EDGES 14         /* sum_{i<4} (2+i), model_search.py:76-81 */
+
+typedef enum pcd_status {
+    PCD_OK = 0,
+    PCD_ERR_ARG = -1,            /* null pointer / inconsistent sizes */
+    PCD_ERR_UNSUPPORTED = -2,    /* shape outside the compiled template set */
+    PCD_ERR_CUDA = -3,           /* launch failed; see pcd_last_cuda_error() */
+    PCD_ERR_ALIGN = -4           /* pointer not 16-byte aligned where required */
+} pcd_status;
+
+int pcd_version(void);
+const char* pcd_strerror(int status);
+/* 1 when the library was compiled by nvcc for sm_100a, 0 for the CPU emulation build used only by
+ * tests/ (tests/emu): the product loader refuses a library that returns 0. */
+int pcd_is_cuda_build(void);
+const char* pcd_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * channel_shuffle(x, groups)                     darts_vqa/pcdarts/model_search.py:14-28
+ * out[:, j*groups + g] = in[:, g*(C/groups) + j]   — bit-exact copy.
+ * ---------------------------------------------------------------------------------------------- */
+int pcd_channel_shuffle(const float* x, float* y, int batch, int channels, int hw, int groups,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cell(steps=4, multiplier=4, C_pp, C_p, C, reduction, reduction_prev).forward(s0, s1, weights,
+ * weights2)                                      darts_vqa/pcdarts/model_search.py:61-94
+ * including its 14 MixedOp.forward (model_search.py:44-58), the candidate ops of operations.py:4-104,
+ * the partial-channel slice / 2x2 max-pool bypass / channel_shuffle, the beta-weighted node sums and
+ * the preprocess ReLUConvBN / FactorizedReduce.
+ *
+ * A MixedOp on its own (MixedOp(C, stride).forward(x, weights)) is the degenerate cell
+ * `pcd_mixedop_*` below: one edge, beta = 1, no preprocess.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pcd_cell_shape {
+    int32_t batch;            /* B */
+    int32_t c_prev_prev;      /* channels of s0 */
+    int32_t c_prev;           /* channels of s1 */
+    int32_t channels;         /* C: channels of every state inside the cell (multiple of 16) */
+    int32_t height, width;    /* spatial size of s1 (s0 is 2x that when reduction_prev) */
+    int32_t reduction;        /* edges from s0/s1 have stride 2 */
+    int32_t reduction_prev;   /* preprocess0 is FactorizedReduce */
+    int32_t steps;            /* must be 4 */
+    float bn_eps;             /* 1e-5 */
+    float bn_momentum;        /* 0.1 */
+} pcd_cell_shape;
+
+/* Sizes of the caller-owned arenas, in elements. */
+typedef struct pcd_cell_sizes {
+    int64_t param_floats;     /* weights, registration order of Cell.named_parameters() */
+    int64_t running_floats;   /* BN running_mean/running_var pairs, registration order */
+    int64_t nbt_int64;        /* BN num_batches_tracked, registration order */
+    int64_t out_floats;       /* B * 4C * Ho * Wo */
+    int64_t saved_floats;     /* activations kept for backward */
+    int64_t stats_doubles;    /* forward BN sums (kept for backward) */
+    int64_t bwd_work_floats;  /* backward scratch */
+    int64_t bwd_stats_doubles;/* backward reduction scratch */
+    int32_t out_height, out_width;
+} pcd_cell_sizes;
+
+int pcd_cell_sizes_of(const pcd_cell_shape* shape, pcd_cell_sizes* out);
+
+typedef struct pcd_cell_fwd_args {
+    pcd_cell_shape shape;
+    const float* s0;          /* (B, C_pp, H0, W0) contiguous */
+    const float* s1;          /* (B, C_p, H, W) contiguous */
+    const float* weights;     /* (14, 8) softmax(alphas) rows, device */
+    const float* weights2;    /* (14,) grouped softmax(betas), device */
+    const float* params;      /* param arena */
+    float* running;           /* running-stat arena (updated) */
+    int64_t* nbt;             /* num_batches_tracked arena (updated) */
+    float* out;               /* (B, 4C, Ho, Wo) contiguous */
+    float* saved;             /* saved arena */
+    double* stats;            /* stats arena (zeroed by the call) */
+} pcd_cell_fwd_args;
+
+int pcd_cell_forward(const pcd_cell_fwd_args* a, void* stream);
+
+typedef struct pcd_cell_bwd_args {
+    pcd_cell_shape shape;
+    const float* s0;
+    const float* s1;
+    const float* weights;
+    const float* weights2;
+    const float* params;
+    const float* out;         /* forward output (the node tensors live in it) */
+    const float* saved;
+    const double* stats;
+    const float* grad_out;    /* (B, 4C, Ho, Wo) contiguous */
+    float* grad_s0;           /* written */
+    float* grad_s1;           /* written */
+    float* grad_weights;      /* (14, 8) written */
+    float* grad_weights2;     /* (14,) written */
+    float* grad_params;       /* param-arena shaped; zeroed then accumulated; may be NULL when
+                                 need_param_grads == 0 (the HVP passes, architect_vqa.py:110,115) */
+    float* work;              /* bwd_work_floats */
+    double* bstats;           /* bwd_stats_doubles (zeroed by the call) */
+    int32_t need_param_grads;
+    int32_t need_input_grads; /* grad_s0/grad_s1 wanted */
+} pcd_cell_bwd_args;
+
+int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MixedOp(C, stride).forward(x, weights)         darts_vqa/pcdarts/model_search.py:30-58
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pcd_mixedop_shape {
+    int32_t batch, channels, height, width, stride;
+    float bn_eps, bn_momentum;
+} pcd_mixedop_shape;
+
+typedef struct pcd_mixedop_sizes {
+    int64_t param_floats, running_floats, nbt_int64, out_floats, saved_floats, stats_doubles,
+            bwd_work_floats, bwd_stats_doubles;
+    int32_t out_height, out_width;
+} pcd_mixedop_sizes;
+
+int pcd_mixedop_sizes_of(const pcd_mixedop_shape* shape, pcd_mixedop_sizes* out);
+
+typedef struct pcd_mixedop_fwd_args {
+    pcd_mixedop_shape shape;
+    const float* x;           /* (B, C, H, W) contiguous */
+    const float* weights;     /* (8,) */
+    const float* params;
+    float* running;
+    int64_t* nbt;
+    float* out;               /* (B, C, H/stride, W/stride) */
+    float* saved;
+    double* stats;
+} pcd_mixedop_fwd_args;
+
+int pcd_mixedop_forward(const pcd_mixedop_fwd_args* a, void* stream);
+
+typedef struct pcd_mixedop_bwd_args {
+    pcd_mixedop_shape shape;
+    const float* x;
+    const float* weights;
+    const float* params;
+    const float* saved;
+    const double* stats;
+    const float* grad_out;
+    float* grad_x;
+    float* grad_weights;      /* (8,) */
+    float* grad_params;
+    float* work;
+    double* bstats;
+    int32_t need_param_grads;
+} pcd_mixedop_bwd_args;
+
+int pcd_mixedop_backward(const pcd_mixedop_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Network.stem = Conv2d(3, 3C, 3, padding=1, bias=False) + BatchNorm2d(3C) (affine)
+ *                                                darts_vqa/pcdarts/model_search.py:110-113,150-151
+ * params arena: conv weight (Cout,3,3,3), bn weight (Cout), bn bias (Cout).
+ * saved: pre-BN conv output z (B,Cout,H,W).  stats: 2*Cout doubles.  bstats: 2*Cout doubles.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pcd_stem_args {
+    int32_t batch, c_out, height, width;
+    float bn_eps, bn_momentum;
+    const float* x;           /* (B,3,H,W) contiguous (the reference expands 1-channel input first) */
+    const float* params;
+    float* running;           /* mean(Cout), var(Cout) */
+    int64_t* nbt;
+    float* out;               /* fwd: written.  bwd: read */
+    float* saved_z;           /* fwd: written.  bwd: read */
+    double* stats;            /* fwd: written.  bwd: read */
+    /* backward only */
+    const float* grad_out;
+    float* grad_x;            /* may be NULL */
+    float* grad_params;       /* zeroed then accumulated; may be NULL */
+    double* bstats;
+} pcd_stem_args;
+
+int pcd_stem_forward(const pcd_stem_args* a, void* stream);
+int pcd_stem_backward(const pcd_stem_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ReLUConvBN(C_in, C_out, 1, 1, 0, affine=False)   darts_vqa/pcdarts/operations.py:22-33
+ * FactorizedReduce(C_in, C_out, affine=False)      darts_vqa/pcdarts/operations.py:90-104
+ * (the Cell preprocess ops, model_search.py:67-71, when used on their own)
+ * weight: [C_out][C_in]; for FactorizedReduce conv_1 rows then conv_2 rows, back to back.
+ * y holds the normalised output; stats (2*C_out doubles) is kept for backward.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pcd_pre_args {
+    int32_t batch, c_in, c_out, height, width;   /* input spatial size */
+    int32_t factorized;                          /* 1 => FactorizedReduce (output is H/2 x W/2) */
+    float bn_eps, bn_momentum;
+    const float* x;
+    const float* weight;
+    float* running;          /* mean(C_out), var(C_out); fwd only */
+    int64_t* nbt;            /* fwd only */
+    float* y;                /* fwd: written.  bwd: read */
+    double* stats;           /* fwd: written.  bwd: read */
+    /* backward only */
+    const float* grad_y;
+    float* grad_x;           /* may be NULL */
+    float* grad_weight;      /* zeroed then accumulated; may be NULL */
+    double* bstats;          /* 2*C_out doubles scratch */
+} pcd_pre_args;
+
+int pcd_preprocess_forward(const pcd_pre_args* a, void* stream);
+int pcd_preprocess_backward(const pcd_pre_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Network.global_pooling = AdaptiveAvgPool2d(7) followed by flatten
+ *                                                darts_vqa/pcdarts/model_search.py:129,176-178
+ * ---------------------------------------------------------------------------------------------- */
+int pcd_adaptive_avgpool_forward(const float* x, float* y, int batch, int channels, int h, int w,
+                                 int oh, int ow, void* stream);
+int pcd_adaptive_avgpool_backward(const float* gy, float* gx, int batch, int channels, int h, int w,
+                                  int oh, int ow, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCDARTS_SM100_H */

@@ -1,0 +1,648 @@
+// pcd_api.cu — launch orchestration and the extern "C" surface declared in include/pcdarts_sm100.h.
+//
+// Built by nvcc (-gencode arch=compute_100a,code=sm_100a) into libpcdarts_sm100.so.  The same file is
+// compiled by g++ with -DPCD_EMU into tests/emu/libpcd_emu.so, where every kernel body runs as nested
+// host loops over (block, task): test infrastructure for the index arithmetic, never a product path
+// (pcd_is_cuda_build() returns 0 there and the product loader refuses it).
+#include "../../include/pcdarts_sm100.h"
+#include "pcd_bwd.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace pcd {
+
+#if PCD_CUDA
+#define PCD_D __device__ __forceinline__
+static thread_local char g_last_err[256] = "";
+
+template <class Body, class Args>
+__global__ void __launch_bounds__(kThreads) pcd_kernel(const Args a) {
+    extern __shared__ F4 pcd_smem4[];
+    Body::run(a, blockIdx.x, blockIdx.y, blockIdx.z, reinterpret_cast<float*>(pcd_smem4));
+}
+
+template <class Body, class Args>
+static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, void* stream) {
+    const size_t bytes = smem_floats * sizeof(float);
+    if (gx <= 0 || gy <= 0 || gz <= 0) return PCD_OK;
+    if (bytes > 227 * 1024) return PCD_ERR_UNSUPPORTED;
+    if (bytes > 48 * 1024) {
+        static thread_local size_t configured = 0;   // per (Body,Args) instantiation
+        if (bytes > configured) {
+            cudaError_t e = cudaFuncSetAttribute(pcd_kernel<Body, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024);
+            if (e != cudaSuccess) {
+                snprintf(g_last_err, sizeof g_last_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                return PCD_ERR_CUDA;
+            }
+            configured = 227 * 1024;
+        }
+    }
+    pcd_kernel<Body, Args><<<dim3(gx, gy, gz), kThreads, bytes, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_last_err, sizeof g_last_err, "launch: %s", cudaGetErrorString(e));
+        return PCD_ERR_CUDA;
+    }
+    return PCD_OK;
+}
+
+static int zero_async(void* p, size_t bytes, void* stream) {
+    if (!bytes) return PCD_OK;
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        snprintf(g_last_err, sizeof g_last_err, "memset: %s", cudaGetErrorString(e));
+        return PCD_ERR_CUDA;
+    }
+    return PCD_OK;
+}
+#else
+#define PCD_D inline
+static char g_last_err[256] = "";
+
+template <class Body, class Args>
+static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, void*) {
+    if (gx <= 0 || gy <= 0 || gz <= 0) return PCD_OK;
+    if (smem_floats * sizeof(float) > 227 * 1024) return PCD_ERR_UNSUPPORTED;
+    float* smem = (float*)aligned_alloc(64, (smem_floats * sizeof(float) + 63) / 64 * 64);
+    for (int z = 0; z < gz; ++z)
+        for (int y = 0; y < gy; ++y)
+            for (int x = 0; x < gx; ++x) {
+                for (size_t i = 0; i < smem_floats; ++i) smem[i] = NAN;   // catch reads of unwritten smem
+                Body::run(a, x, y, z, smem);
+            }
+    free(smem);
+    return PCD_OK;
+}
+
+static int zero_async(void* p, size_t bytes, void*) {
+    memset(p, 0, bytes);
+    return PCD_OK;
+}
+#endif
+
+// ---- kernel body adaptors -----------------------------------------------------------------------------
+template <int C, int S> struct KPassA { static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { passA_body<C, S>(a, x, y, z, sm); } };
+template <int C> struct KPassB { static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { passB_body<C>(a, x, y, z, sm); } };
+template <int C> struct KCombine { static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
+struct KPreConv { static PCD_D void run(const PreArgs& a, int x, int y, int, float* sm) { pre_conv_body(a, x, y, sm); } };
+struct KNorm { static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
+struct KStem { static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
+struct KGapF { static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };
+struct KGapB { static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_bwd_body(a, x); } };
+struct KShuffle { static PCD_D void run(const ShuffleArgs& a, int x, int y, int z, float*) { shuffle_body(a, x, y, z); } };
+template <int C> struct KNodeStats { static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
+template <int C> struct KBwdB { static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdB_body<C>(a, x, y, z, sm); } };
+template <int C, int S> struct KBwdA { static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdA_body<C, S>(a, x, y, z, sm); } };
+struct KSourceGrad { static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
+struct KArchGrads { static PCD_D void run(const ArchGradArgs& a, int, int, int, float*) { arch_grads_body(a); } };
+struct KBnBwdStats { static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
+struct KPreBwd { static PCD_D void run(const PreBwdArgs& a, int x, int, int, float* sm) { pre_bwd_body(a, x, a.nblocks_launch, sm); } };
+struct KStemBwd { static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd_body(a, x, a.nblocks_launch, sm); } };
+
+#define PCD_DISPATCH_C(c, EXPR)                         \
+    do {                                                \
+        if ((c) == 4) { constexpr int CC = 4; EXPR; }   \
+        else if ((c) == 8) { constexpr int CC = 8; EXPR; } \
+        else if ((c) == 16) { constexpr int CC = 16; EXPR; } \
+        else return PCD_ERR_UNSUPPORTED;                \
+    } while (0)
+
+#define PCD_TRY(x) do { int rc_ = (x); if (rc_ != PCD_OK) return rc_; } while (0)
+
+// ---- geometry of one homogeneous group of edges ---------------------------------------------------------
+struct EdgeGeom {
+    int B, c, S, Hs, Ws, Ho, Wo;
+    long long nslot() const { return (long long)B * c * Ho * Wo; }
+};
+
+static int run_passAB(const EdgeGeom& q, const EdgeF* edges, int n, float eps, void* stream) {
+    if (n == 0) return PCD_OK;
+    if (n > kMaxEdgesPerLaunch) return PCD_ERR_ARG;
+    PassArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = q.B; a.Hs = q.Hs; a.Ws = q.Ws; a.Ho = q.Ho; a.Wo = q.Wo; a.S = q.S; a.eps = eps; a.nedges = n;
+    for (int i = 0; i < n; ++i) a.e[i] = edges[i];
+    Tile t = pick_tile(q.Ho, q.Wo, q.c, q.S == 1 ? 4096 : 2048);
+    a.TH = t.TH; a.TW = t.TW; a.tiles_x = t.tiles_x;
+    const int tiles = t.tiles_x * t.tiles_y;
+    if (q.S == 1)
+        PCD_DISPATCH_C(q.c, PCD_TRY((launch<KPassA<CC, 1>, PassArgs>(a, tiles, q.B, n, passA_smem_floats(CC, 1, t.TH, t.TW), stream))));
+    else
+        PCD_DISPATCH_C(q.c, PCD_TRY((launch<KPassA<CC, 2>, PassArgs>(a, tiles, q.B, n, passA_smem_floats(CC, 2, t.TH, t.TW), stream))));
+    Tile tb = pick_tile(q.Ho, q.Wo, q.c, 4096);
+    a.TH = tb.TH; a.TW = tb.TW; a.tiles_x = tb.tiles_x;
+    PCD_DISPATCH_C(q.c, PCD_TRY((launch<KPassB<CC>, PassArgs>(a, tb.tiles_x * tb.tiles_y, q.B, n, passB_smem_floats(CC, tb.TH, tb.TW), stream))));
+    return PCD_OK;
+}
+
+static int run_combine(int B, int c, int Ho, int Wo, float eps, float mom, float* out, long long out_ns,
+                       const EdgeC* edges, int n, void* stream) {
+    if (n > kMaxNodeIn) return PCD_ERR_ARG;
+    CombineArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.Ho = Ho; a.Wo = Wo; a.eps = eps; a.momentum = mom; a.nin = n; a.update_running = 1;
+    a.out = out; a.out_ns = out_ns;
+    for (int i = 0; i < n; ++i) a.e[i] = edges[i];
+    const int chunks = (Ho * Wo + kCombinePx - 1) / kCombinePx;
+    PCD_DISPATCH_C(c, PCD_TRY((launch<KCombine<CC>, CombineArgs>(a, chunks, B, 1, combine_smem_floats(CC), stream))));
+    return PCD_OK;
+}
+
+static int run_node_stats(int B, int c, int Ho, int Wo, const float* dn, long long dn_ns, const EdgeS* edges, int n,
+                          void* stream) {
+    NodeStatsArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.Ho = Ho; a.Wo = Wo; a.px_per_block = 4096 / c; a.dn = dn; a.dn_ns = dn_ns; a.nin = n;
+    for (int i = 0; i < n; ++i) a.e[i] = edges[i];
+    const int chunks = (Ho * Wo + a.px_per_block - 1) / a.px_per_block;
+    PCD_DISPATCH_C(c, PCD_TRY((launch<KNodeStats<CC>, NodeStatsArgs>(a, chunks, B, n, node_stats_smem_floats(CC), stream))));
+    return PCD_OK;
+}
+
+static int run_edge_bwd(const EdgeGeom& q, const EdgeG* edges, int n, float eps, int need_wgrad, void* stream) {
+    if (n == 0) return PCD_OK;
+    if (n > kMaxEdgesPerLaunch) return PCD_ERR_ARG;
+    EdgeBwdArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = q.B; a.Hs = q.Hs; a.Ws = q.Ws; a.Ho = q.Ho; a.Wo = q.Wo; a.S = q.S; a.eps = eps; a.nedges = n;
+    a.need_wgrad = need_wgrad;
+    for (int i = 0; i < n; ++i) a.e[i] = edges[i];
+    Tile tb = pick_tile(q.Ho, q.Wo, q.c, 4096);
+    a.TH = tb.TH; a.TW = tb.TW; a.tiles_x = tb.tiles_x;
+    PCD_DISPATCH_C(q.c, PCD_TRY((launch<KBwdB<CC>, EdgeBwdArgs>(a, tb.tiles_x * tb.tiles_y, q.B, n, bwdB_smem_floats(CC, tb.TH, tb.TW), stream))));
+    Tile t = pick_tile(q.Ho, q.Wo, q.c, q.S == 1 ? 4096 : 2048);
+    a.TH = t.TH; a.TW = t.TW; a.tiles_x = t.tiles_x;
+    const int tiles = t.tiles_x * t.tiles_y;
+    if (q.S == 1)
+        PCD_DISPATCH_C(q.c, PCD_TRY((launch<KBwdA<CC, 1>, EdgeBwdArgs>(a, tiles, q.B, n, bwdA_smem_floats(CC, 1, t.TH, t.TW), stream))));
+    else
+        PCD_DISPATCH_C(q.c, PCD_TRY((launch<KBwdA<CC, 2>, EdgeBwdArgs>(a, tiles, q.B, n, bwdA_smem_floats(CC, 2, t.TH, t.TW), stream))));
+    return PCD_OK;
+}
+
+static int run_source_grad(const SourceGradArgs& a, void* stream) {
+    const int chunks = (a.Hs * a.Ws + 4095) / 4096;
+    return launch<KSourceGrad, SourceGradArgs>(a, chunks, a.C, a.B, 0, stream);
+}
+
+// ---- preprocess ------------------------------------------------------------------------------------------
+static int run_pre_forward(int B, int Cin, int Cout, int Hin, int Win, int fr, float eps, float mom, const float* x,
+                           const float* w, float* y, double* stats, float* running, long long* nbt, void* stream) {
+    if (Cout % kPreCog) return PCD_ERR_UNSUPPORTED;
+    if (fr && ((Hin | Win) & 1)) return PCD_ERR_UNSUPPORTED;
+    PreArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.Cin = Cin; a.Cout = Cout; a.Hin = Hin; a.Win = Win; a.fr = fr;
+    a.Ho = fr ? Hin / 2 : Hin; a.Wo = fr ? Win / 2 : Win;
+    a.eps = eps; a.momentum = mom; a.x = x; a.w = w; a.y = y; a.stats = stats; a.running = running; a.nbt = nbt;
+    const int HW = a.Ho * a.Wo;
+    PCD_TRY((launch<KPreConv, PreArgs>(a, (HW + kPrePx - 1) / kPrePx, B, 1, pre_smem_floats(Cin, Cout), stream)));
+    NormArgs nrm;
+    memset(&nrm, 0, sizeof nrm);
+    nrm.B = B; nrm.C = Cout; nrm.HW = HW; nrm.eps = eps; nrm.momentum = mom; nrm.src = y; nrm.dst = y;
+    nrm.stats = stats; nrm.running = running; nrm.nbt = nbt;
+    return launch<KNorm, NormArgs>(nrm, (HW + 4095) / 4096, Cout, B, 0, stream);
+}
+
+static int run_pre_backward(int B, int Cin, int Cout, int Hin, int Win, int fr, float eps, const float* x, const float* w,
+                            const float* y, const float* dy, const double* stats, double* bstats, float* dx, float* gw,
+                            void* stream) {
+    const int Ho = fr ? Hin / 2 : Hin, Wo = fr ? Win / 2 : Win, HW = Ho * Wo;
+    BnBwdStatArgs s;
+    memset(&s, 0, sizeof s);
+    s.B = B; s.C = Cout; s.HW = HW; s.dy = dy; s.y = y; s.stats = nullptr; s.eps = eps; s.bstats = bstats;
+    PCD_TRY((launch<KBnBwdStats, BnBwdStatArgs>(s, (HW + 4095) / 4096, Cout, B, bn_bwd_stats_smem_floats(), stream)));
+    if (!dx && !gw) return PCD_OK;
+    PreBwdArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.Cin = Cin; a.Cout = Cout; a.Hin = Hin; a.Win = Win; a.Ho = Ho; a.Wo = Wo; a.fr = fr;
+    a.PXB = (Cin >= 128) ? 32 : 64;
+    a.nblocks_px = B * ((HW + a.PXB - 1) / a.PXB);
+    a.nblocks_launch = a.nblocks_px < 296 ? a.nblocks_px : 296;
+    a.x = x; a.w = w; a.y = y; a.dy = dy; a.stats = stats; a.bstats = bstats; a.eps = eps; a.dx = dx; a.gw = gw;
+    return launch<KPreBwd, PreBwdArgs>(a, a.nblocks_launch, 1, 1, pre_bwd_smem_floats(Cin, Cout, a.PXB, fr), stream);
+}
+
+// ---- cell layout -------------------------------------------------------------------------------------------
+struct CellLayout {
+    int B, C, c, Cpp, Cp, Hs, Ws, Ho, Wo, H0, W0, red, redp;
+    int node_of[PCD_MAX_EDGES], src_of[PCD_MAX_EDGES], stride[PCD_MAX_EDGES], first_edge[PCD_MAX_STEPS];
+    long long par[PCD_MAX_EDGES], run[PCD_MAX_EDGES], nbt[PCD_MAX_EDGES], stats[PCD_MAX_EDGES], bstats[PCD_MAX_EDGES];
+    long long saved[PCD_MAX_EDGES], ga[PCD_MAX_EDGES], dxs[PCD_MAX_EDGES];
+    long long pre_par[2], pre_run[2], pre_nbt[2], pre_stats[2], pre_bstats[2], pre_out[2], pre_dout[2];
+    long long dn[PCD_MAX_STEPS];
+    pcd_cell_sizes tot;
+};
+
+static int cell_layout(const pcd_cell_shape& s, CellLayout& L) {
+    if (s.steps != 4) return PCD_ERR_UNSUPPORTED;
+    if (s.channels % 16 || s.batch <= 0 || s.height <= 0 || s.width <= 0) return PCD_ERR_UNSUPPORTED;
+    const int c = s.channels / 4;
+    if (c != 4 && c != 8 && c != 16) return PCD_ERR_UNSUPPORTED;
+    if (s.reduction && ((s.height | s.width) & 1)) return PCD_ERR_UNSUPPORTED;
+    memset(&L, 0, sizeof L);
+    L.B = s.batch; L.C = s.channels; L.c = c; L.Cpp = s.c_prev_prev; L.Cp = s.c_prev;
+    L.Hs = s.height; L.Ws = s.width; L.red = s.reduction; L.redp = s.reduction_prev;
+    L.Ho = s.reduction ? s.height / 2 : s.height;
+    L.Wo = s.reduction ? s.width / 2 : s.width;
+    L.H0 = s.reduction_prev ? 2 * s.height : s.height;
+    L.W0 = s.reduction_prev ? 2 * s.width : s.width;
+    long long par = 0, run = 0, nbt = 0, st = 0, bst = 0, sv = 0, wk = 0;
+    const long long state = (long long)L.B * L.C * L.Hs * L.Ws;
+    const int cin[2] = {L.Cpp, L.Cp};
+    for (int i = 0; i < 2; ++i) {
+        L.pre_par[i] = par; par += (long long)L.C * cin[i];
+        L.pre_run[i] = run; run += 2 * L.C;
+        L.pre_nbt[i] = nbt; nbt += 1;
+        L.pre_stats[i] = st; st += 2 * L.C;
+        L.pre_bstats[i] = bst; bst += 2 * L.C;
+        L.pre_out[i] = sv; sv += state;
+        L.pre_dout[i] = wk; wk += state;
+    }
+    int e = 0;
+    for (int i = 0; i < 4; ++i) {
+        L.first_edge[i] = e;
+        for (int j = 0; j < 2 + i; ++j, ++e) {
+            const int sd = (s.reduction && j < 2) ? 2 : 1;
+            L.node_of[e] = i; L.src_of[e] = j; L.stride[e] = sd;
+            const long long nslot = (long long)L.B * c * L.Ho * L.Wo;
+            const long long in_px = (long long)L.B * c * (sd == 2 ? L.Hs * L.Ws : L.Ho * L.Wo);
+            L.par[e] = par; par += edge_param_floats(c, sd);
+            L.run[e] = run; run += edge_nbn(sd) * 2 * c;
+            L.nbt[e] = nbt; nbt += edge_nbn(sd);
+            L.stats[e] = st; st += edge_stats_doubles(c, sd);
+            L.bstats[e] = bst; bst += edge_bstats_doubles(c);
+            L.saved[e] = sv; sv += edge_nslots(sd) * nslot;
+            L.ga[e] = wk; wk += 2 * nslot;
+            L.dxs[e] = wk; wk += in_px;
+        }
+    }
+    const long long node = (long long)L.B * L.C * L.Ho * L.Wo;
+    for (int i = 0; i < 3; ++i) { L.dn[i] = wk; wk += node; }
+    L.tot.param_floats = par; L.tot.running_floats = run; L.tot.nbt_int64 = nbt;
+    L.tot.out_floats = 4 * node; L.tot.saved_floats = sv; L.tot.stats_doubles = st;
+    L.tot.bwd_work_floats = wk; L.tot.bwd_stats_doubles = bst;
+    L.tot.out_height = L.Ho; L.tot.out_width = L.Wo;
+    return PCD_OK;
+}
+
+struct StateRef { const float* p; long long ns; int H, W; };
+
+static StateRef state_ref(const CellLayout& L, const float* saved, const float* out, int j) {
+    StateRef r;
+    if (j < 2) { r.p = saved + L.pre_out[j]; r.ns = (long long)L.C * L.Hs * L.Ws; r.H = L.Hs; r.W = L.Ws; }
+    else { r.p = out + (long long)(j - 2) * L.C * L.Ho * L.Wo; r.ns = 4LL * L.C * L.Ho * L.Wo; r.H = L.Ho; r.W = L.Wo; }
+    return r;
+}
+
+}  // namespace pcd
+
+using namespace pcd;
+
+extern "C" {
+
+int pcd_version(void) { return PCD_VERSION; }
+int pcd_is_cuda_build(void) { return PCD_CUDA; }
+const char* pcd_last_cuda_error(void) { return g_last_err; }
+const char* pcd_strerror(int s) {
+    switch (s) {
+        case PCD_OK: return "ok";
+        case PCD_ERR_ARG: return "invalid argument";
+        case PCD_ERR_UNSUPPORTED: return "shape not supported by the compiled kernels";
+        case PCD_ERR_CUDA: return "CUDA launch failed";
+        case PCD_ERR_ALIGN: return "pointer not 16-byte aligned";
+        default: return "unknown error";
+    }
+}
+
+int pcd_channel_shuffle(const float* x, float* y, int batch, int channels, int hw, int groups, void* stream) {
+    if (!x || !y || groups <= 0 || channels % groups) return PCD_ERR_ARG;
+    ShuffleArgs a;
+    a.B = batch; a.C = channels; a.HW = hw; a.groups = groups; a.x = x; a.y = y;
+    return launch<KShuffle, ShuffleArgs>(a, (hw + 4095) / 4096, channels, batch, 0, stream);
+}
+
+int pcd_cell_sizes_of(const pcd_cell_shape* shape, pcd_cell_sizes* out) {
+    if (!shape || !out) return PCD_ERR_ARG;
+    CellLayout L;
+    PCD_TRY(cell_layout(*shape, L));
+    *out = L.tot;
+    return PCD_OK;
+}
+
+int pcd_cell_forward(const pcd_cell_fwd_args* a, void* stream) {
+    if (!a || !a->s0 || !a->s1 || !a->weights || !a->weights2 || !a->params || !a->running || !a->nbt || !a->out ||
+        !a->saved || !a->stats)
+        return PCD_ERR_ARG;
+    CellLayout L;
+    PCD_TRY(cell_layout(a->shape, L));
+    if ((((uintptr_t)a->saved) | ((uintptr_t)a->out) | ((uintptr_t)a->params)) & 15) return PCD_ERR_ALIGN;
+    const float eps = a->shape.bn_eps, mom = a->shape.bn_momentum;
+    PCD_TRY(zero_async(a->stats, L.tot.stats_doubles * sizeof(double), stream));
+    PCD_TRY(run_pre_forward(L.B, L.Cpp, L.C, L.H0, L.W0, L.redp, eps, mom, a->s0, a->params + L.pre_par[0],
+                            a->saved + L.pre_out[0], a->stats + L.pre_stats[0], a->running + L.pre_run[0],
+                            (long long*)a->nbt + L.pre_nbt[0], stream));
+    PCD_TRY(run_pre_forward(L.B, L.Cp, L.C, L.Hs, L.Ws, 0, eps, mom, a->s1, a->params + L.pre_par[1],
+                            a->saved + L.pre_out[1], a->stats + L.pre_stats[1], a->running + L.pre_run[1],
+                            (long long*)a->nbt + L.pre_nbt[1], stream));
+    // wave w: edges whose source is state (w == 0 ? {s0,s1} : node w-1); then node w is complete
+    for (int w = 0; w < 4; ++w) {
+        EdgeF ef[kMaxEdgesPerLaunch];
+        int n = 0;
+        EdgeGeom q;
+        q.B = L.B; q.c = L.c;
+        for (int e = 0; e < PCD_MAX_EDGES; ++e) {
+            const int j = L.src_of[e];
+            if ((w == 0) ? (j >= 2) : (j != w + 1)) continue;
+            StateRef s = state_ref(L, a->saved, a->out, j);
+            ef[n].x = s.p; ef[n].x_ns = s.ns;
+            ef[n].par = a->params + L.par[e];
+            ef[n].saved = a->saved + L.saved[e];
+            ef[n].stats = a->stats + L.stats[e];
+            q.S = L.stride[e]; q.Hs = s.H; q.Ws = s.W;
+            ++n;
+        }
+        q.Ho = L.Ho; q.Wo = L.Wo;
+        PCD_TRY(run_passAB(q, ef, n, eps, stream));
+        EdgeC ec[kMaxNodeIn];
+        const int e0 = L.first_edge[w];
+        for (int j = 0; j < 2 + w; ++j) {
+            const int e = e0 + j;
+            StateRef s = state_ref(L, a->saved, a->out, j);
+            ec[j].x = s.p; ec[j].x_ns = s.ns; ec[j].stride = L.stride[e]; ec[j].Hs = s.H; ec[j].Ws = s.W;
+            ec[j].saved = a->saved + L.saved[e];
+            ec[j].stats = a->stats + L.stats[e];
+            ec[j].alpha = a->weights + e * PCD_NUM_PRIMITIVES;
+            ec[j].beta = a->weights2 + e;
+            ec[j].running = a->running + L.run[e];
+            ec[j].nbt = (long long*)a->nbt + L.nbt[e];
+        }
+        PCD_TRY(run_combine(L.B, L.c, L.Ho, L.Wo, eps, mom, a->out + (long long)w * L.C * L.Ho * L.Wo,
+                            4LL * L.C * L.Ho * L.Wo, ec, 2 + w, stream));
+    }
+    return PCD_OK;
+}
+
+int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
+    if (!a || !a->s0 || !a->s1 || !a->weights || !a->weights2 || !a->params || !a->out || !a->saved || !a->stats ||
+        !a->grad_out || !a->grad_weights || !a->grad_weights2 || !a->work || !a->bstats)
+        return PCD_ERR_ARG;
+    if (a->need_param_grads && !a->grad_params) return PCD_ERR_ARG;
+    if (a->need_input_grads && (!a->grad_s0 || !a->grad_s1)) return PCD_ERR_ARG;
+    CellLayout L;
+    PCD_TRY(cell_layout(a->shape, L));
+    const float eps = a->shape.bn_eps;
+    const long long node = (long long)L.B * L.C * L.Ho * L.Wo;
+    PCD_TRY(zero_async(a->bstats, L.tot.bwd_stats_doubles * sizeof(double), stream));
+    if (a->need_param_grads) PCD_TRY(zero_async(a->grad_params, L.tot.param_floats * sizeof(float), stream));
+    auto dn_ptr = [&](int i, long long& ns) -> const float* {
+        if (i == 3) { ns = 4 * (node / L.B); return a->grad_out + 3 * (node / L.B); }
+        ns = node / L.B;
+        return a->work + L.dn[i];
+    };
+    for (int i = 3; i >= 0; --i) {
+        long long dn_ns;
+        const float* dn = dn_ptr(i, dn_ns);
+        // 1. reductions over node i's incoming edges
+        EdgeS es[kMaxNodeIn];
+        const int e0 = L.first_edge[i];
+        for (int j = 0; j < 2 + i; ++j) {
+            const int e = e0 + j;
+            StateRef s = state_ref(L, a->saved, a->out, j);
+            es[j].x = s.p; es[j].x_ns = s.ns; es[j].stride = L.stride[e]; es[j].Hs = s.H; es[j].Ws = s.W;
+            es[j].saved = a->saved + L.saved[e];
+            es[j].bstats = a->bstats + L.bstats[e];
+        }
+        PCD_TRY(run_node_stats(L.B, L.c, L.Ho, L.Wo, dn, dn_ns, es, 2 + i, stream));
+        // 2. every edge whose source is state (i == 0 ? {s0,s1} : node i-1) now has its consumer's sums
+        EdgeG eg[kMaxEdgesPerLaunch];
+        int n = 0;
+        EdgeGeom q;
+        q.B = L.B; q.c = L.c; q.Ho = L.Ho; q.Wo = L.Wo;
+        for (int e = 0; e < PCD_MAX_EDGES; ++e) {
+            const int j = L.src_of[e];
+            if ((i == 0) ? (j >= 2) : (j != i + 1)) continue;
+            StateRef s = state_ref(L, a->saved, a->out, j);
+            long long cns;
+            const float* cdn = dn_ptr(L.node_of[e], cns);
+            eg[n].x = s.p; eg[n].x_ns = s.ns; eg[n].dn = cdn; eg[n].dn_ns = cns;
+            eg[n].saved = a->saved + L.saved[e];
+            eg[n].stats = a->stats + L.stats[e];
+            eg[n].bstats = a->bstats + L.bstats[e];
+            eg[n].par = a->params + L.par[e];
+            eg[n].gpar = a->need_param_grads ? a->grad_params + L.par[e] : nullptr;
+            eg[n].alpha = a->weights + e * PCD_NUM_PRIMITIVES;
+            eg[n].beta = a->weights2 + e;
+            eg[n].ga = a->work + L.ga[e];
+            eg[n].dxs = a->work + L.dxs[e];
+            q.S = L.stride[e]; q.Hs = s.H; q.Ws = s.W;
+            ++n;
+        }
+        PCD_TRY(run_edge_bwd(q, eg, n, eps, a->need_param_grads, stream));
+        // 3. gradient of the source state(s)
+        for (int j = (i == 0 ? 0 : i + 1); j <= (i == 0 ? 1 : i + 1); ++j) {
+            StateRef s = state_ref(L, a->saved, a->out, j);
+            SourceGradArgs sg;
+            memset(&sg, 0, sizeof sg);
+            sg.B = L.B; sg.C = L.C; sg.Hs = s.H; sg.Ws = s.W; sg.x = s.p; sg.x_ns = s.ns;
+            if (j >= 2) {
+                sg.g0 = a->grad_out + (long long)(j - 2) * (node / L.B); sg.g0_ns = 4 * (node / L.B);
+                sg.out = a->work + L.dn[j - 2]; sg.out_ns = node / L.B;
+            } else {
+                sg.g0 = nullptr;
+                sg.out = a->work + L.pre_dout[j]; sg.out_ns = (long long)L.C * L.Hs * L.Ws;
+            }
+            int m = 0;
+            for (int e = 0; e < PCD_MAX_EDGES; ++e) {
+                if (L.src_of[e] != j) continue;
+                if (m >= kMaxSrcEdges) return PCD_ERR_ARG;
+                long long cns;
+                const float* cdn = dn_ptr(L.node_of[e], cns);
+                sg.e[m].dxs = a->work + L.dxs[e]; sg.e[m].dn = cdn; sg.e[m].dn_ns = cns;
+                sg.e[m].beta = a->weights2 + e; sg.e[m].stride = L.stride[e];
+                ++m;
+            }
+            sg.nedges = m;
+            PCD_TRY(run_source_grad(sg, stream));
+        }
+    }
+    // 4. d softmax(alpha) rows, d beta
+    ArchGradArgs ag;
+    memset(&ag, 0, sizeof ag);
+    ag.c = L.c; ag.nedges = PCD_MAX_EDGES; ag.eps = eps;
+    for (int e = 0; e < PCD_MAX_EDGES; ++e) {
+        ag.e[e].stats = a->stats + L.stats[e];
+        ag.e[e].bstats = a->bstats + L.bstats[e];
+        ag.e[e].alpha = a->weights + e * PCD_NUM_PRIMITIVES;
+        ag.e[e].beta = a->weights2 + e;
+        ag.e[e].stride = L.stride[e];
+        ag.e[e].count = (double)L.B * L.Ho * L.Wo;
+        ag.e[e].gw = a->grad_weights + e * PCD_NUM_PRIMITIVES;
+        ag.e[e].gw2 = a->grad_weights2 + e;
+    }
+    PCD_TRY((launch<KArchGrads, ArchGradArgs>(ag, 1, 1, 1, 0, stream)));
+    // 5. preprocess backward
+    PCD_TRY(run_pre_backward(L.B, L.Cpp, L.C, L.H0, L.W0, L.redp, eps, a->s0, a->params + L.pre_par[0],
+                             a->saved + L.pre_out[0], a->work + L.pre_dout[0], a->stats + L.pre_stats[0],
+                             a->bstats + L.pre_bstats[0], a->need_input_grads ? a->grad_s0 : nullptr,
+                             a->need_param_grads ? a->grad_params + L.pre_par[0] : nullptr, stream));
+    PCD_TRY(run_pre_backward(L.B, L.Cp, L.C, L.Hs, L.Ws, 0, eps, a->s1, a->params + L.pre_par[1],
+                             a->saved + L.pre_out[1], a->work + L.pre_dout[1], a->stats + L.pre_stats[1],
+                             a->bstats + L.pre_bstats[1], a->need_input_grads ? a->grad_s1 : nullptr,
+                             a->need_param_grads ? a->grad_params + L.pre_par[1] : nullptr, stream));
+    return PCD_OK;
+}
+
+// ---- MixedOp on its own --------------------------------------------------------------------------------
+static int mixedop_geom(const pcd_mixedop_shape& s, EdgeGeom& q) {
+    if (s.channels % 16 || (s.stride != 1 && s.stride != 2) || s.batch <= 0) return PCD_ERR_UNSUPPORTED;
+    const int c = s.channels / 4;
+    if (c != 4 && c != 8 && c != 16) return PCD_ERR_UNSUPPORTED;
+    if (s.stride == 2 && ((s.height | s.width) & 1)) return PCD_ERR_UNSUPPORTED;
+    q.B = s.batch; q.c = c; q.S = s.stride; q.Hs = s.height; q.Ws = s.width;
+    q.Ho = s.height / s.stride; q.Wo = s.width / s.stride;
+    return PCD_OK;
+}
+
+int pcd_mixedop_sizes_of(const pcd_mixedop_shape* s, pcd_mixedop_sizes* o) {
+    if (!s || !o) return PCD_ERR_ARG;
+    EdgeGeom q;
+    PCD_TRY(mixedop_geom(*s, q));
+    o->param_floats = edge_param_floats(q.c, q.S);
+    o->running_floats = edge_nbn(q.S) * 2 * q.c;
+    o->nbt_int64 = edge_nbn(q.S);
+    o->out_floats = 4 * q.nslot();
+    o->saved_floats = edge_nslots(q.S) * q.nslot();
+    o->stats_doubles = edge_stats_doubles(q.c, q.S);
+    o->bwd_work_floats = 2 * q.nslot() + (long long)q.B * q.c * q.Hs * q.Ws;
+    o->bwd_stats_doubles = edge_bstats_doubles(q.c);
+    o->out_height = q.Ho; o->out_width = q.Wo;
+    return PCD_OK;
+}
+
+int pcd_mixedop_forward(const pcd_mixedop_fwd_args* a, void* stream) {
+    if (!a || !a->x || !a->weights || !a->params || !a->running || !a->nbt || !a->out || !a->saved || !a->stats)
+        return PCD_ERR_ARG;
+    EdgeGeom q;
+    PCD_TRY(mixedop_geom(a->shape, q));
+    if ((((uintptr_t)a->saved) | ((uintptr_t)a->out) | ((uintptr_t)a->params)) & 15) return PCD_ERR_ALIGN;
+    const long long C = 4LL * q.c;
+    PCD_TRY(zero_async(a->stats, edge_stats_doubles(q.c, q.S) * sizeof(double), stream));
+    EdgeF ef;
+    ef.x = a->x; ef.x_ns = C * q.Hs * q.Ws; ef.par = a->params; ef.saved = a->saved; ef.stats = a->stats;
+    PCD_TRY(run_passAB(q, &ef, 1, a->shape.bn_eps, stream));
+    EdgeC ec;
+    memset(&ec, 0, sizeof ec);
+    ec.x = a->x; ec.x_ns = ef.x_ns; ec.stride = q.S; ec.Hs = q.Hs; ec.Ws = q.Ws; ec.saved = a->saved; ec.stats = a->stats;
+    ec.alpha = a->weights; ec.beta = nullptr; ec.running = a->running; ec.nbt = (long long*)a->nbt;
+    return run_combine(q.B, q.c, q.Ho, q.Wo, a->shape.bn_eps, a->shape.bn_momentum, a->out, C * q.Ho * q.Wo, &ec, 1, stream);
+}
+
+int pcd_mixedop_backward(const pcd_mixedop_bwd_args* a, void* stream) {
+    if (!a || !a->x || !a->weights || !a->params || !a->saved || !a->stats || !a->grad_out || !a->grad_x ||
+        !a->grad_weights || !a->work || !a->bstats)
+        return PCD_ERR_ARG;
+    if (a->need_param_grads && !a->grad_params) return PCD_ERR_ARG;
+    EdgeGeom q;
+    PCD_TRY(mixedop_geom(a->shape, q));
+    const long long C = 4LL * q.c;
+    PCD_TRY(zero_async(a->bstats, edge_bstats_doubles(q.c) * sizeof(double), stream));
+    if (a->need_param_grads) PCD_TRY(zero_async(a->grad_params, edge_param_floats(q.c, q.S) * sizeof(float), stream));
+    EdgeS es;
+    memset(&es, 0, sizeof es);
+    es.x = a->x; es.x_ns = C * q.Hs * q.Ws; es.stride = q.S; es.Hs = q.Hs; es.Ws = q.Ws; es.saved = a->saved; es.bstats = a->bstats;
+    PCD_TRY(run_node_stats(q.B, q.c, q.Ho, q.Wo, a->grad_out, C * q.Ho * q.Wo, &es, 1, stream));
+    EdgeG eg;
+    memset(&eg, 0, sizeof eg);
+    eg.x = a->x; eg.x_ns = es.x_ns; eg.dn = a->grad_out; eg.dn_ns = C * q.Ho * q.Wo; eg.saved = a->saved; eg.stats = a->stats;
+    eg.bstats = a->bstats; eg.par = a->params; eg.gpar = a->need_param_grads ? a->grad_params : nullptr;
+    eg.alpha = a->weights; eg.beta = nullptr; eg.ga = a->work; eg.dxs = a->work + 2 * q.nslot();
+    PCD_TRY(run_edge_bwd(q, &eg, 1, a->shape.bn_eps, a->need_param_grads, stream));
+    SourceGradArgs sg;
+    memset(&sg, 0, sizeof sg);
+    sg.B = q.B; sg.C = (int)C; sg.Hs = q.Hs; sg.Ws = q.Ws; sg.x = a->x; sg.x_ns = es.x_ns; sg.g0 = nullptr;
+    sg.out = a->grad_x; sg.out_ns = es.x_ns; sg.nedges = 1;
+    sg.e[0].dxs = eg.dxs; sg.e[0].dn = a->grad_out; sg.e[0].dn_ns = eg.dn_ns; sg.e[0].beta = nullptr; sg.e[0].stride = q.S;
+    PCD_TRY(run_source_grad(sg, stream));
+    ArchGradArgs ag;
+    memset(&ag, 0, sizeof ag);
+    ag.c = q.c; ag.nedges = 1; ag.eps = a->shape.bn_eps;
+    ag.e[0].stats = a->stats; ag.e[0].bstats = a->bstats; ag.e[0].alpha = a->weights; ag.e[0].beta = nullptr;
+    ag.e[0].stride = q.S; ag.e[0].count = (double)q.B * q.Ho * q.Wo; ag.e[0].gw = a->grad_weights; ag.e[0].gw2 = nullptr;
+    return launch<KArchGrads, ArchGradArgs>(ag, 1, 1, 1, 0, stream);
+}
+
+// ---- stem ---------------------------------------------------------------------------------------------------
+int pcd_stem_forward(const pcd_stem_args* a, void* stream) {
+    if (!a || !a->x || !a->params || !a->running || !a->nbt || !a->out || !a->saved_z || !a->stats) return PCD_ERR_ARG;
+    if (a->c_out % 8) return PCD_ERR_UNSUPPORTED;
+    const int HW = a->height * a->width, Co = a->c_out;
+    PCD_TRY(zero_async(a->stats, 2 * Co * sizeof(double), stream));
+    StemArgs s;
+    s.B = a->batch; s.Cout = Co; s.H = a->height; s.W = a->width; s.x = a->x; s.w = a->params; s.z = a->saved_z; s.stats = a->stats;
+    PCD_TRY((launch<KStem, StemArgs>(s, (HW + kStemPx - 1) / kStemPx, a->batch, 1, stem_smem_floats(Co), stream)));
+    NormArgs n;
+    memset(&n, 0, sizeof n);
+    n.B = a->batch; n.C = Co; n.HW = HW; n.eps = a->bn_eps; n.momentum = a->bn_momentum; n.src = a->saved_z; n.dst = a->out;
+    n.stats = a->stats; n.gamma = a->params + Co * 27; n.bias = a->params + Co * 28; n.running = a->running;
+    n.nbt = (long long*)a->nbt;
+    return launch<KNorm, NormArgs>(n, (HW + 4095) / 4096, Co, a->batch, 0, stream);
+}
+
+int pcd_stem_backward(const pcd_stem_args* a, void* stream) {
+    if (!a || !a->x || !a->params || !a->saved_z || !a->stats || !a->grad_out || !a->bstats) return PCD_ERR_ARG;
+    if (a->grad_x) return PCD_ERR_UNSUPPORTED;   // the image never requires grad on this path
+    const int HW = a->height * a->width, Co = a->c_out;
+    PCD_TRY(zero_async(a->bstats, 2 * Co * sizeof(double), stream));
+    BnBwdStatArgs s;
+    memset(&s, 0, sizeof s);
+    s.B = a->batch; s.C = Co; s.HW = HW; s.dy = a->grad_out; s.y = a->saved_z; s.stats = a->stats; s.eps = a->bn_eps;
+    s.bstats = a->bstats;
+    PCD_TRY((launch<KBnBwdStats, BnBwdStatArgs>(s, (HW + 4095) / 4096, Co, a->batch, bn_bwd_stats_smem_floats(), stream)));
+    if (!a->grad_params) return PCD_OK;
+    PCD_TRY(zero_async(a->grad_params, (size_t)Co * 29 * sizeof(float), stream));
+    StemBwdArgs b;
+    memset(&b, 0, sizeof b);
+    b.B = a->batch; b.Cout = Co; b.H = a->height; b.W = a->width; b.PXB = 64;
+    b.nblocks_px = a->batch * ((HW + 63) / 64);
+    b.nblocks_launch = b.nblocks_px < 296 ? b.nblocks_px : 296;
+    b.x = a->x; b.z = a->saved_z; b.dy = a->grad_out; b.gamma = a->params + Co * 27; b.stats = a->stats; b.bstats = a->bstats;
+    b.eps = a->bn_eps; b.gw = a->grad_params; b.ggamma = a->grad_params + Co * 27; b.gbias = a->grad_params + Co * 28;
+    return launch<KStemBwd, StemBwdArgs>(b, b.nblocks_launch, 1, 1, stem_bwd_smem_floats(Co, 64), stream);
+}
+
+int pcd_preprocess_forward(const pcd_pre_args* a, void* stream) {
+    if (!a || !a->x || !a->weight || !a->running || !a->nbt || !a->y || !a->stats) return PCD_ERR_ARG;
+    PCD_TRY(zero_async(a->stats, 2 * a->c_out * sizeof(double), stream));
+    return run_pre_forward(a->batch, a->c_in, a->c_out, a->height, a->width, a->factorized, a->bn_eps, a->bn_momentum,
+                           a->x, a->weight, a->y, a->stats, a->running, (long long*)a->nbt, stream);
+}
+
+int pcd_preprocess_backward(const pcd_pre_args* a, void* stream) {
+    if (!a || !a->x || !a->weight || !a->y || !a->stats || !a->grad_y || !a->bstats) return PCD_ERR_ARG;
+    PCD_TRY(zero_async(a->bstats, 2 * a->c_out * sizeof(double), stream));
+    if (a->grad_weight) PCD_TRY(zero_async(a->grad_weight, (size_t)a->c_out * a->c_in * sizeof(float), stream));
+    return run_pre_backward(a->batch, a->c_in, a->c_out, a->height, a->width, a->factorized, a->bn_eps, a->x, a->weight,
+                            a->y, a->grad_y, a->stats, a->bstats, a->grad_x, a->grad_weight, stream);
+}
+
+int pcd_adaptive_avgpool_forward(const float* x, float* y, int batch, int channels, int h, int w, int oh, int ow, void* stream) {
+    if (!x || !y) return PCD_ERR_ARG;
+    GapArgs a;
+    a.B = batch; a.C = channels; a.H = h; a.W = w; a.OH = oh; a.OW = ow; a.x = x; a.y = y;
+    const long long total = (long long)batch * channels * oh * ow;
+    return launch<KGapF, GapArgs>(a, (int)((total + kThreads - 1) / kThreads), 1, 1, 0, stream);
+}
+
+int pcd_adaptive_avgpool_backward(const float* gy, float* gx, int batch, int channels, int h, int w, int oh, int ow, void* stream) {
+    if (!gy || !gx) return PCD_ERR_ARG;
+    GapArgs a;
+    a.B = batch; a.C = channels; a.H = h; a.W = w; a.OH = oh; a.OW = ow; a.x = gy; a.y = gx;
+    const long long total = (long long)batch * channels * h * w;
+    return launch<KGapB, GapArgs>(a, (int)((total + kThreads - 1) / kThreads), 1, 1, 0, stream);
+}
+
+}  // extern "C"

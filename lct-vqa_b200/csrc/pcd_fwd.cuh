@@ -1,0 +1,663 @@
+// pcd_fwd.cuh — forward kernel bodies (see pcd_common.cuh for the phase discipline).
+//
+// Forward of one MixedOp edge (model_search.py:44-58) is split at the BatchNorm batch-statistic
+// barriers into
+//   passA   : xs tile -> max/avg pool, FactorizedReduce, first halves of the separable convs and both
+//             dilated convs (depthwise -> pointwise), + per-channel sum / sum^2 of every pre-BN tensor
+//   passB   : BN+ReLU of the sep-conv mid tensors on load -> second depthwise/pointwise pair + stats
+//   combine : per NODE: sum over incoming edges of beta * [ sum_k w_k BN(op_k) | bypass ] written
+//             channel-shuffled straight into the node's slice of the cell output (model_search.py:90)
+#pragma once
+#include "pcd_common.cuh"
+
+namespace pcd {
+
+struct EdgeF {
+    const float* x;        // source state (B, C, Hs, Ws)
+    long long x_ns;        // its batch stride (floats)
+    const float* par;      // edge parameter block
+    float* saved;          // edge saved-activation slots
+    double* stats;         // edge forward sums
+};
+
+struct PassArgs {
+    int B, Hs, Ws, Ho, Wo, S;
+    int TH, TW, tiles_x;
+    float eps;
+    int nedges;
+    EdgeF e[kMaxEdgesPerLaunch];
+};
+
+struct Geo {
+    int n, oy0, ox0, TH, TW, Ho, Wo;
+};
+
+PCD_HD long long out_index(const Geo& g, int C, int ch, int oy, int ox) {
+    return (((long long)g.n * C + ch) * g.Ho + oy) * g.Wo + ox;
+}
+
+// store 4 consecutive pixels of row oy starting at ox (masked at the image edge)
+PCD_HD void store4(float* base, const Geo& g, int C, int ch, int oy, int ox, const float (&v)[4]) {
+    if (oy >= g.Ho) return;
+    float* p = base + out_index(g, C, ch, oy, ox);
+    if (ox + 3 < g.Wo && (((uintptr_t)p) & 15) == 0) {
+        F4 t = {v[0], v[1], v[2], v[3]};
+        *reinterpret_cast<F4*>(p) = t;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (ox + j < g.Wo) p[j] = v[j];
+    }
+}
+
+// One depthwise->pointwise unit on a shared-memory input tile.
+//   plane tile: [C][rows][pitch], column origin at image col S*ox0-4, row origin at image row S*oy0-halo_y
+template <int C, int KS, int DIL, int S, bool RELU>
+PCD_HD void unit_forward(const float* tile, int rows, int pitch, int halo_y, const float* w_dw,
+                         const float* w_pw, float* T, float* P, float* P2, float* t_out, float* z_out,
+                         double* st /* sum[C], sumsq[C] of this BN */, const Geo& g) {
+    constexpr int PAD = DIL * (KS - 1) / 2;
+    const int TH = g.TH, TW = g.TW, NPIX = TH * TW, NSTRIP = NPIX / 4, PW4 = TW / 4;
+    const int NPATCH = (TH / 4) * PW4;
+    PCD_FOR(task, C * NPATCH) {
+        const int ch = task / NPATCH, patch = task - ch * NPATCH;
+        const int py = (patch / PW4) * 4, px = (patch % PW4) * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        dw_patch<KS, DIL, S, false, RELU>(tile + ch * rows * pitch, pitch, S * py - PAD + halo_y, S * px,
+                                          w_dw + ch * KS * KS, acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            F4 v = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+            *reinterpret_cast<F4*>(T + ch * NPIX + (py + i) * TW + px) = v;
+            store4(t_out, g, C, ch, g.oy0 + py + i, g.ox0 + px, acc[i]);
+        }
+    }
+    PCD_SYNC();
+    constexpr int NCG = C / 4;
+    PCD_FOR(task, NCG * NSTRIP) {
+        const int cg = task / NSTRIP, strip = task - cg * NSTRIP;
+        const int oyl = strip / PW4, oxl = (strip - oyl * PW4) * 4;
+        float z[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[i][j] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const F4 t = *reinterpret_cast<const F4*>(T + ci * NPIX + strip * 4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float w = w_pw[(cg * 4 + i) * C + ci];
+                z[i][0] = fmaf(w, t.x, z[i][0]);
+                z[i][1] = fmaf(w, t.y, z[i][1]);
+                z[i][2] = fmaf(w, t.z, z[i][2]);
+                z[i][3] = fmaf(w, t.w, z[i][3]);
+            }
+        }
+        const int oy = g.oy0 + oyl, ox = g.ox0 + oxl;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            store4(z_out, g, C, cg * 4 + i, oy, ox, z[i]);
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (oy < g.Ho && ox + j < g.Wo) {
+                    s += z[i][j];
+                    q = fmaf(z[i][j], z[i][j], q);
+                }
+            P[(2 * i) * (NCG * NSTRIP) + task] = s;
+            P[(2 * i + 1) * (NCG * NSTRIP) + task] = q;
+        }
+    }
+    reduce_columns(P, P2, 8, NCG, NSTRIP, NCG * NSTRIP, [&](int grp, int k, float v) {
+        pcd_atomic_add(st + (k & 1) * C + grp * 4 + (k >> 1), (double)v);
+    });
+}
+
+PCD_HOSTDEV size_t passA_smem_floats(int C, int S, int TH, int TW) {
+    const int IH = S * TH + 8, IW = S * TW + 8;
+    return (size_t)C * IH * IW + (size_t)C * TH * TW * 2 + 4 * C * 32 + 64;
+}
+
+template <int C, int S>
+PCD_HD void passA_body(const PassArgs& a, int bx, int n, int ez, float* smem) {
+    const EdgeF& e = a.e[ez];
+    Geo g;
+    g.n = n; g.TH = a.TH; g.TW = a.TW; g.Ho = a.Ho; g.Wo = a.Wo;
+    g.oy0 = (bx / a.tiles_x) * a.TH;
+    g.ox0 = (bx % a.tiles_x) * a.TW;
+    const int TH = a.TH, TW = a.TW, NPIX = TH * TW, NSTRIP = NPIX / 4, PW4 = TW / 4;
+    const int IH = S * TH + 8, IW = S * TW + 8;
+    const int iy0 = S * g.oy0 - 4, ix0 = S * g.ox0 - 4;
+    float* XIN = smem;
+    float* T = XIN + C * IH * IW;
+    float* P = T + C * NPIX;
+    float* P2 = P + C * NPIX;
+    const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
+    const float* xg = e.x + (long long)n * e.x_ns;
+
+    PCD_FOR(i, C * IH * IW) {
+        const int ch = i / (IH * IW), r = (i / IW) % IH, col = i % IW;
+        const int gy = iy0 + r, gx = ix0 + col;
+        float v = 0.f;
+        if (gy >= 0 && gy < a.Hs && gx >= 0 && gx < a.Ws) v = xg[((long long)ch * a.Hs + gy) * a.Ws + gx];
+        XIN[i] = v;
+    }
+    PCD_SYNC();
+
+    // ---- 3x3 max / avg pool (operations.py:6-7), stride S, pad 1, count_include_pad=False --------
+    PCD_FOR(task, C * NSTRIP) {
+        const int ch = task / NSTRIP, strip = task - ch * NSTRIP;
+        const int oyl = strip / PW4, oxl = (strip - oyl * PW4) * 4;
+        const float* pl = XIN + ch * IH * IW;
+        float mx[4], av[4];
+        float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
+        const int oy = g.oy0 + oyl;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ox = g.ox0 + oxl + j;
+            float m = -INFINITY, s = 0.f;
+            int cnt = 0;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int gy = S * oy + dy - 1, gx = S * ox + dx - 1;
+                    if (gy >= 0 && gy < a.Hs && gx >= 0 && gx < a.Ws) {
+                        const float v = pl[(S * oyl + dy + 3) * IW + S * (oxl + j) + dx + 3];
+                        m = v > m ? v : m;
+                        s += v;
+                        ++cnt;
+                    }
+                }
+            mx[j] = cnt ? m : 0.f;
+            av[j] = cnt ? s / (float)cnt : 0.f;
+            if (oy < a.Ho && ox < a.Wo) {
+                s1 += mx[j]; q1 = fmaf(mx[j], mx[j], q1);
+                s2 += av[j]; q2 = fmaf(av[j], av[j], q2);
+            }
+        }
+        store4(e.saved + slot_p1() * nslot, g, C, ch, oy, g.ox0 + oxl, mx);
+        store4(e.saved + slot_p2() * nslot, g, C, ch, oy, g.ox0 + oxl, av);
+        const int NT = C * NSTRIP;
+        P[0 * NT + task] = s1; P[1 * NT + task] = q1; P[2 * NT + task] = s2; P[3 * NT + task] = q2;
+    }
+    reduce_columns(P, P2, 4, C, NSTRIP, C * NSTRIP, [&](int ch, int k, float v) {
+        const int bn = (k < 2) ? bn_p1() : bn_p2();
+        pcd_atomic_add(e.stats + (bn * 2 + (k & 1)) * C + ch, (double)v);
+    });
+
+    // ---- skip_connect at stride 2 = FactorizedReduce (operations.py:90-104) ----------------------
+    if (S == 2) {
+        PCD_FOR(task, C * NSTRIP) {
+            const int co = task / NSTRIP, strip = task - co * NSTRIP;
+            const int oyl = strip / PW4, oxl = (strip - oyl * PW4) * 4;
+            const int off = (co >= C / 2) ? 1 : 0;
+            const float* w = e.par + co * C;
+            float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                const float* pl = XIN + ci * IH * IW + (2 * oyl + off + 4) * IW + 2 * oxl + off + 4;
+                const float wv = w[ci];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = fmaf(wv, relu(pl[2 * j]), f[j]);
+            }
+            const int oy = g.oy0 + oyl, ox = g.ox0 + oxl;
+            store4(e.saved + slot_f() * nslot, g, C, co, oy, ox, f);
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (oy < a.Ho && ox + j < a.Wo) { s += f[j]; q = fmaf(f[j], f[j], q); }
+            const int NT = C * NSTRIP;
+            P[task] = s; P[NT + task] = q;
+        }
+        reduce_columns(P, P2, 2, C, NSTRIP, C * NSTRIP, [&](int ch, int k, float v) {
+            pcd_atomic_add(e.stats + (bn_f() * 2 + k) * C + ch, (double)v);
+        });
+    }
+
+    // ---- A3, A5 (first half of SepConv, operations.py:55-58), D3, D5 (DilConv, :40-43) -----------
+#define PCD_UNIT_A(U, KS, DIL)                                                                        \
+    unit_forward<C, KS, DIL, S, true>(XIN, IH, IW, 4, e.par + edge_dw_off(C, S, U),                   \
+                                      e.par + edge_pw_off(C, S, U), T, P, P2,                         \
+                                      e.saved + slot_t(U) * nslot, e.saved + slot_z(U) * nslot,       \
+                                      e.stats + bn_unit(S, U) * 2 * C, g)
+    PCD_UNIT_A(0, 3, 1);
+    PCD_UNIT_A(2, 5, 1);
+    PCD_UNIT_A(4, 3, 2);
+    PCD_UNIT_A(5, 5, 2);
+#undef PCD_UNIT_A
+}
+
+PCD_HOSTDEV size_t passB_smem_floats(int C, int TH, int TW) {
+    return (size_t)C * (TH + 8) * (TW + 8) + (size_t)C * TH * TW * 2 + 4 * C * 32 + 2 * C + 64;
+}
+
+// second half of SepConv: BN -> ReLU -> dw (stride 1) -> pw   (operations.py:58-62)
+template <int C>
+PCD_HD void passB_body(const PassArgs& a, int bx, int n, int ez, float* smem) {
+    const EdgeF& e = a.e[ez];
+    Geo g;
+    g.n = n; g.TH = a.TH; g.TW = a.TW; g.Ho = a.Ho; g.Wo = a.Wo;
+    g.oy0 = (bx / a.tiles_x) * a.TH;
+    g.ox0 = (bx % a.tiles_x) * a.TW;
+    const int TH = a.TH, TW = a.TW, NPIX = TH * TW;
+    const int IH = TH + 8, IW = TW + 8;
+    float* Q = smem;
+    float* T = Q + C * IH * IW;
+    float* P = T + C * NPIX;
+    float* P2 = P + C * NPIX;
+    float* BNC = P2 + 4 * C * 32;
+    const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
+    const double cnt = (double)a.B * a.Ho * a.Wo;
+    const int S = a.S;
+    for (int half = 0; half < 2; ++half) {
+        const int uA = half ? 2 : 0, uB = uA + 1;
+        PCD_FOR(j, C) {
+            BnC b = bn_consts(e.stats, C, bn_unit(S, uA), j, cnt, a.eps);
+            BNC[2 * j] = b.mean;
+            BNC[2 * j + 1] = b.rstd;
+        }
+        PCD_SYNC();
+        const float* zA = e.saved + slot_z(uA) * nslot;
+        PCD_FOR(i, C * IH * IW) {
+            const int ch = i / (IH * IW), r = (i / IW) % IH, col = i % IW;
+            const int gy = g.oy0 - 4 + r, gx = g.ox0 - 4 + col;
+            float v = 0.f;
+            if (gy >= 0 && gy < a.Ho && gx >= 0 && gx < a.Wo)
+                v = relu((zA[(((long long)n * C + ch) * a.Ho + gy) * a.Wo + gx] - BNC[2 * ch]) * BNC[2 * ch + 1]);
+            Q[i] = v;
+        }
+        PCD_SYNC();
+        if (half == 0)
+            unit_forward<C, 3, 1, 1, false>(Q, IH, IW, 4, e.par + edge_dw_off(C, S, uB), e.par + edge_pw_off(C, S, uB),
+                                            T, P, P2, e.saved + slot_t(uB) * nslot, e.saved + slot_z(uB) * nslot,
+                                            e.stats + bn_unit(S, uB) * 2 * C, g);
+        else
+            unit_forward<C, 5, 1, 1, false>(Q, IH, IW, 4, e.par + edge_dw_off(C, S, uB), e.par + edge_pw_off(C, S, uB),
+                                            T, P, P2, e.saved + slot_t(uB) * nslot, e.saved + slot_z(uB) * nslot,
+                                            e.stats + bn_unit(S, uB) * 2 * C, g);
+    }
+}
+
+// ---- node combine ---------------------------------------------------------------------------------
+struct EdgeC {
+    const float* x;
+    long long x_ns;
+    int stride, Hs, Ws;
+    const float* saved;
+    const double* stats;
+    const float* alpha;    // 8 softmaxed op weights (device)
+    const float* beta;     // 1 scalar (device) or null => 1
+    float* running;        // BN running stats of this edge (updated once per forward)
+    long long* nbt;
+};
+
+constexpr int kMaxNodeIn = 5;
+
+struct CombineArgs {
+    int B, Ho, Wo;
+    float eps, momentum;
+    int nin, update_running;
+    float* out;            // node tensor (B, C, Ho, Wo) view
+    long long out_ns;
+    EdgeC e[kMaxNodeIn];
+};
+
+constexpr int kCombinePx = 1024;
+
+PCD_HOSTDEV size_t combine_smem_floats(int C) { return (size_t)kMaxNodeIn * 8 * C + 16; }
+
+// coefficient rows per edge: 0 P1, 1 P2, 2 B3, 3 B5, 4 D3, 5 D5, 6 F (stride 2) or identity (stride 1), 7 shift
+template <int C>
+PCD_HD void combine_body(const CombineArgs& a, int bx, int n, float* smem) {
+    float* COEF = smem;
+    const double cnt = (double)a.B * a.Ho * a.Wo;
+    const int HW = a.Ho * a.Wo;
+    PCD_FOR(i, a.nin * C) {
+        const int ei = i / C, j = i - ei * C;
+        const EdgeC& e = a.e[ei];
+        const float beta = e.beta ? e.beta[0] : 1.f;
+        const int s = e.stride;
+        const int bns[6] = {bn_p1(), bn_p2(), bn_unit(s, 1), bn_unit(s, 3), bn_unit(s, 4), bn_unit(s, 5)};
+        const int prim[6] = {1, 2, 4, 5, 6, 7};
+        float shift = 0.f;
+        float* co = COEF + ei * 8 * C;
+        for (int k = 0; k < 6; ++k) {
+            BnC b = bn_consts(e.stats, C, bns[k], j, cnt, a.eps);
+            const float sc = beta * e.alpha[prim[k]] * b.rstd;
+            co[k * C + j] = sc;
+            shift -= sc * b.mean;
+        }
+        if (s == 2) {
+            BnC b = bn_consts(e.stats, C, bn_f(), j, cnt, a.eps);
+            const float sc = beta * e.alpha[3] * b.rstd;
+            co[6 * C + j] = sc;
+            shift -= sc * b.mean;
+        } else {
+            co[6 * C + j] = beta * e.alpha[3];
+        }
+        co[7 * C + j] = shift;
+    }
+    PCD_SYNC();
+    const int p0 = bx * kCombinePx;
+    const int npx = (HW - p0) < kCombinePx ? (HW - p0) : kCombinePx;
+    const int nstrip = (npx + 3) / 4;
+    const long long nslot = (long long)a.B * C * HW;
+    PCD_FOR(task, C * nstrip) {
+        const int j = task / nstrip, strip = task - j * nstrip;
+        const int p = p0 + strip * 4;
+        float m[4] = {0.f, 0.f, 0.f, 0.f}, by[3][4];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) by[q][t] = 0.f;
+        for (int ei = 0; ei < a.nin; ++ei) {
+            const EdgeC& e = a.e[ei];
+            const float* co = COEF + ei * 8 * C;
+            const float beta = e.beta ? e.beta[0] : 1.f;
+            const long long so = ((long long)n * C + j) * HW + p;
+            const int slots[6] = {slot_p1(), slot_p2(), slot_z(1), slot_z(3), slot_z(4), slot_z(5)};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (p + t >= HW) break;
+                float acc = co[7 * C + j];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc = fmaf(co[k * C + j], e.saved[slots[k] * nslot + so + t], acc);
+                if (e.stride == 1) {
+                    const float* xb = e.x + (long long)n * e.x_ns;
+                    acc = fmaf(co[6 * C + j], xb[(long long)j * HW + p + t], acc);
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) by[q - 1][t] = fmaf(beta, xb[(long long)(q * C + j) * HW + p + t], by[q - 1][t]);
+                } else {
+                    acc = fmaf(co[6 * C + j], e.saved[slot_f() * nslot + so + t], acc);
+                    const int oy = (p + t) / a.Wo, ox = (p + t) - oy * a.Wo;
+                    const float* xb = e.x + (long long)n * e.x_ns;
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) {
+                        const float* pl = xb + (long long)(q * C + j) * e.Hs * e.Ws + (2 * oy) * e.Ws + 2 * ox;
+                        float v = pl[0];
+                        v = pl[1] > v ? pl[1] : v;
+                        v = pl[e.Ws] > v ? pl[e.Ws] : v;
+                        v = pl[e.Ws + 1] > v ? pl[e.Ws + 1] : v;
+                        by[q - 1][t] = fmaf(beta, v, by[q - 1][t]);
+                    }
+                }
+                m[t] += acc;
+            }
+        }
+        float* ob = a.out + (long long)n * a.out_ns;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (p + t >= HW) break;
+            ob[(long long)(4 * j + 0) * HW + p + t] = m[t];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) ob[(long long)(4 * j + q) * HW + p + t] = by[q - 1][t];
+        }
+    }
+    if (a.update_running && bx == 0 && n == 0) {
+        PCD_FOR(i, a.nin * 9 * C) {
+            const int ei = i / (9 * C), bn = (i / C) % 9, j = i % C;
+            const EdgeC& e = a.e[ei];
+            if (bn < edge_nbn(e.stride))
+                bn_running_update(e.stats + bn * 2 * C, C, j, cnt, a.momentum, e.running + bn * 2 * C);
+        }
+        PCD_FOR(i, a.nin * 9) {
+            const int ei = i / 9, bn = i % 9;
+            if (bn < edge_nbn(a.e[ei].stride)) a.e[ei].nbt[bn] += 1;
+        }
+    }
+}
+
+// ---- preprocess: ReLU -> 1x1 conv (ReLUConvBN operations.py:22-33) or FactorizedReduce (:90-104) ----
+struct PreArgs {
+    int B, Cin, Cout, Hin, Win, Ho, Wo, fr;   // fr: 1 => FactorizedReduce (Ho = Hin/2)
+    float eps, momentum;
+    const float* x;      // (B, Cin, Hin, Win) contiguous
+    const float* w;      // RCB: [Cout][Cin]; FR: conv_1 [Cout/2][Cin] then conv_2 [Cout/2][Cin]
+    float* y;            // (B, Cout, Ho, Wo): conv output, normalised in place by pre_norm
+    double* stats;       // sum[Cout], sumsq[Cout]
+    float* running;
+    long long* nbt;
+};
+
+constexpr int kPrePx = 512;     // pixels per block
+constexpr int kPreCog = 8;      // output channels per task
+
+PCD_HOSTDEV size_t pre_smem_floats(int Cin, int Cout) {
+    return (size_t)Cin * Cout + (size_t)16 * (Cout / kPreCog) * (kPrePx / 4) + 16 * (Cout / kPreCog) * 32 + 16;
+}
+
+PCD_HD void pre_conv_body(const PreArgs& a, int bx, int n, float* smem) {
+    const int Cin = a.Cin, Cout = a.Cout, HW = a.Ho * a.Wo, NCG = Cout / kPreCog;
+    float* W = smem;
+    float* P = W + Cin * Cout;
+    const int p0 = bx * kPrePx;
+    const int npx = (HW - p0) < kPrePx ? (HW - p0) : kPrePx;
+    const int nstrip = (npx + 3) / 4, NSTRIPMAX = kPrePx / 4;
+    float* P2 = P + 16 * NCG * NSTRIPMAX;
+    PCD_FOR(i, Cin * Cout) W[i] = a.w[i];
+    PCD_SYNC();
+    const float* xb = a.x + (long long)n * Cin * a.Hin * a.Win;
+    const int NT = NCG * NSTRIPMAX;
+    PCD_FOR(task, NCG * NSTRIPMAX) {
+        const int cg = task / NSTRIPMAX, strip = task - cg * NSTRIPMAX;
+        float acc[kPreCog][4];
+#pragma unroll
+        for (int i = 0; i < kPreCog; ++i)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[i][t] = 0.f;
+        const int p = p0 + strip * 4;
+        if (strip < nstrip) {
+            long long off[4];
+            const int shift = (a.fr && cg * kPreCog >= Cout / 2) ? 1 : 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int pp = (p + t < HW) ? p + t : HW - 1;
+                if (a.fr) {
+                    const int oy = pp / a.Wo, ox = pp - oy * a.Wo;
+                    off[t] = (long long)(2 * oy + shift) * a.Win + 2 * ox + shift;
+                } else {
+                    off[t] = pp;
+                }
+            }
+            const long long cs = (long long)a.Hin * a.Win;
+            for (int ci = 0; ci < Cin; ++ci) {
+                float v[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[t] = relu(xb[ci * cs + off[t]]);
+#pragma unroll
+                for (int i = 0; i < kPreCog; ++i) {
+                    const float w = W[(cg * kPreCog + i) * Cin + ci];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[i][t] = fmaf(w, v[t], acc[i][t]);
+                }
+            }
+            float* yb = a.y + ((long long)n * Cout + cg * kPreCog) * HW;
+#pragma unroll
+            for (int i = 0; i < kPreCog; ++i)
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (p + t < HW) yb[(long long)i * HW + p + t] = acc[i][t];
+        }
+#pragma unroll
+        for (int i = 0; i < kPreCog; ++i) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (strip < nstrip && p + t < HW) { s += acc[i][t]; q = fmaf(acc[i][t], acc[i][t], q); }
+            P[(2 * i) * NT + task] = s;
+            P[(2 * i + 1) * NT + task] = q;
+        }
+    }
+    reduce_columns(P, P2, 16, NCG, NSTRIPMAX, NT, [&](int grp, int k, float v) {
+        pcd_atomic_add(a.stats + (k & 1) * Cout + grp * kPreCog + (k >> 1), (double)v);
+    });
+}
+
+// y = (y - mean) * rstd in place (+ optional affine), running-stat update by block (0,0)
+struct NormArgs {
+    int B, C, HW;
+    float eps, momentum;
+    const float* src;    // pre-BN tensor
+    float* dst;          // may alias src
+    const double* stats;
+    const float* gamma;  // null => 1
+    const float* bias;   // null => 0
+    float* running;
+    long long* nbt;
+};
+
+PCD_HD void norm_body(const NormArgs& a, int bx, int ch, int n) {
+    const double cnt = (double)a.B * a.HW;
+    BnC b = bn_consts(a.stats, a.C, 0, ch, cnt, a.eps);
+    const float sc = b.rstd * (a.gamma ? a.gamma[ch] : 1.f);
+    const float sh = (a.bias ? a.bias[ch] : 0.f) - b.mean * sc;
+    const long long base = ((long long)n * a.C + ch) * a.HW;
+    const int p0 = bx * 4096;
+    const int npx = (a.HW - p0) < 4096 ? (a.HW - p0) : 4096;
+    PCD_FOR(i, npx) a.dst[base + p0 + i] = fmaf(a.src[base + p0 + i], sc, sh);
+    if (bx == 0 && n == 0 && a.running) {
+        PCD_FOR(i, 1) {
+            bn_running_update(a.stats, a.C, ch, cnt, a.momentum, a.running);
+            if (ch == 0) a.nbt[0] += 1;
+        }
+    }
+}
+
+// ---- stem: Conv2d(3, Cout, 3, padding=1) (model_search.py:110-113); BN applied by norm_body ----------
+struct StemArgs {
+    int B, Cout, H, W;
+    const float* x;   // (B,3,H,W)
+    const float* w;   // (Cout,3,3,3)
+    float* z;         // (B,Cout,H,W)
+    double* stats;
+};
+
+constexpr int kStemPx = 512;
+
+PCD_HOSTDEV size_t stem_smem_floats(int Cout) {
+    return (size_t)Cout * 27 + (size_t)16 * (Cout / 8) * (kStemPx / 4) + 16 * (Cout / 8) * 32 + 16;
+}
+
+PCD_HD void stem_conv_body(const StemArgs& a, int bx, int n, float* smem) {
+    const int Cout = a.Cout, HW = a.H * a.W, NCG = Cout / 8, NSTRIPMAX = kStemPx / 4;
+    float* Wt = smem;
+    float* P = Wt + Cout * 27;
+    float* P2 = P + 16 * NCG * NSTRIPMAX;
+    PCD_FOR(i, Cout * 27) Wt[i] = a.w[i];
+    PCD_SYNC();
+    const int p0 = bx * kStemPx;
+    const int NT = NCG * NSTRIPMAX;
+    const float* xb = a.x + (long long)n * 3 * HW;
+    PCD_FOR(task, NT) {
+        const int cg = task / NSTRIPMAX, strip = task - cg * NSTRIPMAX;
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[i][t] = 0.f;
+        const int p = p0 + strip * 4;
+        for (int t = 0; t < 4; ++t) {
+            if (p + t >= HW) break;
+            const int oy = (p + t) / a.W, ox = (p + t) - oy * a.W;
+            for (int ci = 0; ci < 3; ++ci)
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int gy = oy + ky - 1, gx = ox + kx - 1;
+                        if (gy < 0 || gy >= a.H || gx < 0 || gx >= a.W) continue;
+                        const float v = xb[(long long)ci * HW + gy * a.W + gx];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            acc[i][t] = fmaf(Wt[(cg * 8 + i) * 27 + ci * 9 + ky * 3 + kx], v, acc[i][t]);
+                    }
+        }
+        float* zb = a.z + ((long long)n * Cout + cg * 8) * HW;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (p + t < HW) {
+                    zb[(long long)i * HW + p + t] = acc[i][t];
+                    s += acc[i][t];
+                    q = fmaf(acc[i][t], acc[i][t], q);
+                }
+            P[(2 * i) * NT + task] = s;
+            P[(2 * i + 1) * NT + task] = q;
+        }
+    }
+    reduce_columns(P, P2, 16, NCG, NSTRIPMAX, NT, [&](int grp, int k, float v) {
+        pcd_atomic_add(a.stats + (k & 1) * Cout + grp * 8 + (k >> 1), (double)v);
+    });
+}
+
+// ---- AdaptiveAvgPool2d (model_search.py:129,176) -----------------------------------------------------
+struct GapArgs {
+    int B, C, H, W, OH, OW;
+    const float* x;
+    float* y;
+};
+
+PCD_HD void gap_fwd_body(const GapArgs& a, int bx) {
+    const long long total = (long long)a.B * a.C * a.OH * a.OW;
+    PCD_FOR(t, kThreads) {
+        const long long i = (long long)bx * kThreads + t;
+        if (i < total) {
+            const int ox = (int)(i % a.OW), oy = (int)((i / a.OW) % a.OH);
+            const long long nc = i / (a.OW * a.OH);
+            const int y0 = (oy * a.H) / a.OH, y1 = ((oy + 1) * a.H + a.OH - 1) / a.OH;
+            const int x0 = (ox * a.W) / a.OW, x1 = ((ox + 1) * a.W + a.OW - 1) / a.OW;
+            float s = 0.f;
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) s += a.x[(nc * a.H + y) * a.W + x];
+            a.y[i] = s / (float)((y1 - y0) * (x1 - x0));
+        }
+    }
+}
+
+// gx[nc][y][x] = sum over output windows containing (y,x) of gy / window size
+PCD_HD void gap_bwd_body(const GapArgs& a /* x = gy (OHxOW), y = gx (HxW) */, int bx) {
+    const long long total = (long long)a.B * a.C * a.H * a.W;
+    PCD_FOR(t, kThreads) {
+        const long long i = (long long)bx * kThreads + t;
+        if (i < total) {
+            const int x = (int)(i % a.W), y = (int)((i / a.W) % a.H);
+            const long long nc = i / (a.W * a.H);
+            float s = 0.f;
+            for (int oy = 0; oy < a.OH; ++oy) {
+                const int y0 = (oy * a.H) / a.OH, y1 = ((oy + 1) * a.H + a.OH - 1) / a.OH;
+                if (y < y0 || y >= y1) continue;
+                for (int ox = 0; ox < a.OW; ++ox) {
+                    const int x0 = (ox * a.W) / a.OW, x1 = ((ox + 1) * a.W + a.OW - 1) / a.OW;
+                    if (x < x0 || x >= x1) continue;
+                    s += a.x[(nc * a.OH + oy) * a.OW + ox] / (float)((y1 - y0) * (x1 - x0));
+                }
+            }
+            a.y[i] = s;
+        }
+    }
+}
+
+// ---- channel_shuffle (model_search.py:14-28) ----------------------------------------------------------
+struct ShuffleArgs {
+    int B, C, HW, groups;
+    const float* x;
+    float* y;
+};
+
+PCD_HD void shuffle_body(const ShuffleArgs& a, int bx, int oc, int n) {
+    const int per = a.C / a.groups;
+    const int ic = (oc % a.groups) * per + oc / a.groups;
+    const float* src = a.x + ((long long)n * a.C + ic) * a.HW;
+    float* dst = a.y + ((long long)n * a.C + oc) * a.HW;
+    const int p0 = bx * 4096;
+    const int npx = (a.HW - p0) < 4096 ? (a.HW - p0) : 4096;
+    PCD_FOR(i, npx) dst[p0 + i] = src[p0 + i];
+}
+
+}  // namespace pcd

@@ -1,0 +1,404 @@
+"""torch.autograd.Function wrappers over the C ABI, and the flat parameter arenas they rely on.
+
+Boundary: one Function per fused unit — stem, Cell (14 MixedOps + node sums +
+preprocess), stand-alone MixedOp, adaptive pool.  All device memory (outputs, saved activations,
+scratch) is allocated here with torch and handed to the library as raw pointers; the library
+enqueues on torch's current stream.
+"""
+import ctypes as C
+
+import torch
+
+import pcd_native as N
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# --------------------------------------------------------------------------------------------
+# flat arenas: the kernels address a module's weights / BN buffers as ONE contiguous block in
+# registration order; the nn.Parameter / buffer tensors stay ordinary leaves whose .data are views.
+# --------------------------------------------------------------------------------------------
+_LAYOUT_EPOCH = [0]
+
+
+def bump_layout_epoch():
+    """Called from Module._apply overrides: .to()/.cuda()/.float() replace storages (and buffer objects)."""
+    _LAYOUT_EPOCH[0] += 1
+
+
+def _is_run(tensors):
+    """True when the tensors sit back to back in memory in the given order."""
+    nxt = None
+    for t in tensors:
+        if not t.is_contiguous():
+            return False
+        p = t.data_ptr()
+        if nxt is not None and p != nxt:
+            return False
+        nxt = p + t.numel() * t.element_size()
+    return True
+
+
+def _flatten_(tensors):
+    """Rebind every tensor's .data to a view of one new flat tensor (values preserved)."""
+    t0 = tensors[0]
+    total = sum(t.numel() for t in tensors)
+    flat = torch.empty(total, dtype=t0.dtype, device=t0.device)   # allocator blocks are >= 64-byte aligned
+    off = 0
+    with torch.no_grad():
+        for t in tensors:
+            n = t.numel()
+            view = flat[off:off + n].view(t.shape)
+            view.copy_(t.detach())
+            t.data = view
+            off += n
+    return flat
+
+
+class Arena:
+    """Contiguity manager for a root module (Network, or a Cell / MixedOp used on its own)."""
+
+    def __init__(self, module):
+        self.module = module
+        self.valid = False
+        self.epoch = -1
+
+    def _collect(self):
+        m = self.module
+        self.params = list(m.parameters())
+        bufs = list(m.named_buffers())
+        self.running = [b for k, b in bufs if not k.endswith("num_batches_tracked")]
+        self.nbt = [b for k, b in bufs if k.endswith("num_batches_tracked")]
+
+    def ensure(self):
+        """Cheap when nothing moved: two pointer compares per group; full check after .to()/load."""
+        if self.valid and self.epoch == _LAYOUT_EPOCH[0]:
+            ok = True
+            for group, first, last in self._ends:
+                if group[0].data_ptr() != first or group[-1].data_ptr() != last:
+                    ok = False
+                    break
+            if ok:
+                return self
+        self._collect()
+        self._keep = []
+        for group in (self.params, self.running, self.nbt):
+            if group and (not _is_run(group) or group[0].data_ptr() % 16):
+                self._keep.append(_flatten_(group))
+        self._ends = [(g, g[0].data_ptr(), g[-1].data_ptr()) for g in (self.params, self.running, self.nbt) if g]
+        self.param_ptr = self.params[0].data_ptr()
+        self.running_ptr = self.running[0].data_ptr()
+        self.nbt_ptr = self.nbt[0].data_ptr()
+        self.param_floats = sum(p.numel() for p in self.params)
+        self.valid = True
+        self.epoch = _LAYOUT_EPOCH[0]
+        return self
+
+    def invalidate(self):
+        self.valid = False
+
+
+def _views(flat, params):
+    """Split a flat grad arena into per-parameter views (one C++ call + cheap reshapes)."""
+    parts = flat.split_with_sizes([p.numel() for p in params])
+    return [g.view(p.shape) for g, p in zip(parts, params)]
+
+
+def _f32c(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        raise TypeError("pcdarts_sm100 kernels are fp32 only")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# Cell
+# --------------------------------------------------------------------------------------------
+class CellHandle:
+    """Static description of one cell + where its arenas start (byte pointers)."""
+
+    def __init__(self, c_prev_prev, c_prev, channels, reduction, reduction_prev):
+        self.cfg = (c_prev_prev, c_prev, channels, int(bool(reduction)), int(bool(reduction_prev)))
+        self._sizes = {}
+        self.param_ptr = self.running_ptr = self.nbt_ptr = None
+
+    def shape(self, batch, height, width):
+        cpp, cp, ch, red, redp = self.cfg
+        return N.CellShape(batch, cpp, cp, ch, height, width, red, redp, 4, BN_EPS, BN_MOMENTUM)
+
+    def sizes(self, lib, batch, height, width):
+        key = (batch, height, width)
+        if key not in self._sizes:
+            sz = N.CellSizes()
+            sh = self.shape(batch, height, width)
+            N.check(lib, lib.pcd_cell_sizes_of(C.byref(sh), C.byref(sz)), "pcd_cell_sizes_of")
+            self._sizes[key] = sz
+        return self._sizes[key]
+
+
+class CellFunction(torch.autograd.Function):
+    """Cell.forward (model_search.py:83-94) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, s0, s1, weights, weights2, handle, *params):
+        lib = N.lib_for(s1)
+        s0c, s1c, w, w2 = _f32c(s0), _f32c(s1), _f32c(weights), _f32c(weights2)
+        B, _, H, W = s1c.shape
+        sz = handle.sizes(lib, B, H, W)
+        dev = s1c.device
+        out = torch.empty((B, 4 * handle.cfg[2], sz.out_height, sz.out_width), dtype=torch.float32, device=dev)
+        saved = torch.empty(sz.saved_floats, dtype=torch.float32, device=dev)
+        stats = torch.empty(sz.stats_doubles, dtype=torch.float64, device=dev)
+        a = N.CellFwdArgs(handle.shape(B, H, W), N.ptr(s0c), N.ptr(s1c), N.ptr(w), N.ptr(w2), handle.param_ptr,
+                          handle.running_ptr, handle.nbt_ptr, N.ptr(out), N.ptr(saved), N.ptr(stats))
+        N.check(lib, lib.pcd_cell_forward(C.byref(a), N.stream_for(s1c)), "pcd_cell_forward")
+        ctx.handle, ctx.params, ctx.geom = handle, params, (B, H, W)
+        ctx.save_for_backward(s0c, s1c, w, w2, out, saved, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        s0, s1, w, w2, out, saved, stats = ctx.saved_tensors
+        handle, params = ctx.handle, ctx.params
+        lib = N.lib_for(s1)
+        B, H, W = ctx.geom
+        sz = handle.sizes(lib, B, H, W)
+        dev = s1.device
+        gout = _f32c(gout)
+        need_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_par = any(ctx.needs_input_grad[5:])
+        gs0 = torch.empty_like(s0) if need_in else None
+        gs1 = torch.empty_like(s1) if need_in else None
+        gw = torch.empty_like(w)
+        gw2 = torch.empty_like(w2)
+        gpar = torch.empty(sz.param_floats, dtype=torch.float32, device=dev) if need_par else None
+        work = torch.empty(sz.bwd_work_floats, dtype=torch.float32, device=dev)
+        bstats = torch.empty(sz.bwd_stats_doubles, dtype=torch.float64, device=dev)
+        a = N.CellBwdArgs(handle.shape(B, H, W), N.ptr(s0), N.ptr(s1), N.ptr(w), N.ptr(w2), handle.param_ptr,
+                          N.ptr(out), N.ptr(saved), N.ptr(stats), N.ptr(gout), N.ptr(gs0), N.ptr(gs1), N.ptr(gw),
+                          N.ptr(gw2), N.ptr(gpar), N.ptr(work), N.ptr(bstats), int(need_par), int(need_in))
+        N.check(lib, lib.pcd_cell_backward(C.byref(a), N.stream_for(s1)), "pcd_cell_backward")
+        pg = _views(gpar, params) if need_par else [None] * len(params)
+        return (gs0, gs1, gw, gw2, None, *pg)
+
+
+# --------------------------------------------------------------------------------------------
+# MixedOp on its own
+# --------------------------------------------------------------------------------------------
+class MixedHandle:
+    def __init__(self, channels, stride):
+        self.channels, self.stride = channels, stride
+        self._sizes = {}
+        self.param_ptr = self.running_ptr = self.nbt_ptr = None
+
+    def shape(self, B, H, W):
+        return N.MixedShape(B, self.channels, H, W, self.stride, BN_EPS, BN_MOMENTUM)
+
+    def sizes(self, lib, B, H, W):
+        key = (B, H, W)
+        if key not in self._sizes:
+            sz = N.MixedSizes()
+            sh = self.shape(B, H, W)
+            N.check(lib, lib.pcd_mixedop_sizes_of(C.byref(sh), C.byref(sz)), "pcd_mixedop_sizes_of")
+            self._sizes[key] = sz
+        return self._sizes[key]
+
+
+class MixedOpFunction(torch.autograd.Function):
+    """MixedOp.forward (model_search.py:44-58) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, x, weights, handle, *params):
+        lib = N.lib_for(x)
+        xc, w = _f32c(x), _f32c(weights)
+        B, Cc, H, W = xc.shape
+        sz = handle.sizes(lib, B, H, W)
+        dev = xc.device
+        out = torch.empty((B, Cc, sz.out_height, sz.out_width), dtype=torch.float32, device=dev)
+        saved = torch.empty(sz.saved_floats, dtype=torch.float32, device=dev)
+        stats = torch.empty(sz.stats_doubles, dtype=torch.float64, device=dev)
+        a = N.MixedFwdArgs(handle.shape(B, H, W), N.ptr(xc), N.ptr(w), handle.param_ptr, handle.running_ptr,
+                           handle.nbt_ptr, N.ptr(out), N.ptr(saved), N.ptr(stats))
+        N.check(lib, lib.pcd_mixedop_forward(C.byref(a), N.stream_for(xc)), "pcd_mixedop_forward")
+        ctx.handle, ctx.params, ctx.geom = handle, params, (B, H, W)
+        ctx.save_for_backward(xc, w, saved, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w, saved, stats = ctx.saved_tensors
+        handle, params = ctx.handle, ctx.params
+        lib = N.lib_for(x)
+        B, H, W = ctx.geom
+        sz = handle.sizes(lib, B, H, W)
+        dev = x.device
+        gout = _f32c(gout)
+        need_par = any(ctx.needs_input_grad[3:])
+        gx = torch.empty_like(x)
+        gw = torch.empty_like(w)
+        gpar = torch.empty(sz.param_floats, dtype=torch.float32, device=dev) if need_par else None
+        work = torch.empty(sz.bwd_work_floats, dtype=torch.float32, device=dev)
+        bstats = torch.empty(sz.bwd_stats_doubles, dtype=torch.float64, device=dev)
+        a = N.MixedBwdArgs(handle.shape(B, H, W), N.ptr(x), N.ptr(w), handle.param_ptr, N.ptr(saved), N.ptr(stats),
+                           N.ptr(gout), N.ptr(gx), N.ptr(gw), N.ptr(gpar), N.ptr(work), N.ptr(bstats), int(need_par))
+        N.check(lib, lib.pcd_mixedop_backward(C.byref(a), N.stream_for(x)), "pcd_mixedop_backward")
+        pg = _views(gpar, params) if need_par else [None] * len(params)
+        return (gx, gw, None, *pg)
+
+
+# --------------------------------------------------------------------------------------------
+# stem, adaptive pool, shuffle
+# --------------------------------------------------------------------------------------------
+class StemFunction(torch.autograd.Function):
+    """Network.stem (model_search.py:110-113): Conv2d(3, 3C, 3, pad 1) + affine BatchNorm2d."""
+
+    @staticmethod
+    def forward(ctx, x, ptrs, conv_w, bn_w, bn_b):
+        lib = N.lib_for(x)
+        xc = _f32c(x)
+        B, cin, H, W = xc.shape
+        if cin != 3:
+            raise ValueError("stem expects 3 input channels")
+        cout = conv_w.shape[0]
+        dev = xc.device
+        out = torch.empty((B, cout, H, W), dtype=torch.float32, device=dev)
+        z = torch.empty_like(out)
+        stats = torch.empty(2 * cout, dtype=torch.float64, device=dev)
+        a = N.StemArgs(B, cout, H, W, BN_EPS, BN_MOMENTUM, N.ptr(xc), ptrs[0], ptrs[1], ptrs[2], N.ptr(out), N.ptr(z),
+                       N.ptr(stats), None, None, None, None)
+        N.check(lib, lib.pcd_stem_forward(C.byref(a), N.stream_for(xc)), "pcd_stem_forward")
+        ctx.ptrs, ctx.meta = ptrs, (B, cout, H, W)
+        ctx.shapes = (conv_w.shape, bn_w.shape, bn_b.shape)
+        ctx.save_for_backward(xc, z, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, z, stats = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("gradient w.r.t. the image is not part of the search path")
+        lib = N.lib_for(x)
+        B, cout, H, W = ctx.meta
+        gout = _f32c(gout)
+        need_par = any(ctx.needs_input_grad[2:])
+        if not need_par:
+            return (None, None, None, None, None)
+        gpar = torch.empty(cout * 29, dtype=torch.float32, device=x.device)
+        bstats = torch.empty(2 * cout, dtype=torch.float64, device=x.device)
+        a = N.StemArgs(B, cout, H, W, BN_EPS, BN_MOMENTUM, N.ptr(x), ctx.ptrs[0], None, None, None, N.ptr(z),
+                       N.ptr(stats), N.ptr(gout), None, N.ptr(gpar), N.ptr(bstats))
+        N.check(lib, lib.pcd_stem_backward(C.byref(a), N.stream_for(x)), "pcd_stem_backward")
+        gw, gg, gb = gpar.split_with_sizes([cout * 27, cout, cout])
+        return (None, None, gw.view(ctx.shapes[0]), gg, gb)
+
+
+class AdaptiveAvgPoolFunction(torch.autograd.Function):
+    """Network.global_pooling (model_search.py:129,176)."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        lib = N.lib_for(x)
+        xc = _f32c(x)
+        B, Cc, H, W = xc.shape
+        y = torch.empty((B, Cc, size, size), dtype=torch.float32, device=xc.device)
+        N.check(lib, lib.pcd_adaptive_avgpool_forward(N.ptr(xc), N.ptr(y), B, Cc, H, W, size, size, N.stream_for(xc)),
+                "pcd_adaptive_avgpool_forward")
+        ctx.meta = (B, Cc, H, W, size)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        B, Cc, H, W, size = ctx.meta
+        lib = N.lib_for(gy)
+        gy = _f32c(gy)
+        gx = torch.empty((B, Cc, H, W), dtype=torch.float32, device=gy.device)
+        N.check(lib, lib.pcd_adaptive_avgpool_backward(N.ptr(gy), N.ptr(gx), B, Cc, H, W, size, size, N.stream_for(gy)),
+                "pcd_adaptive_avgpool_backward")
+        return gx, None
+
+
+class ChannelShuffleFunction(torch.autograd.Function):
+    """channel_shuffle (model_search.py:14-28); backward is the inverse permutation."""
+
+    @staticmethod
+    def forward(ctx, x, groups):
+        lib = N.lib_for(x)
+        xc = _f32c(x)
+        B, Cc, H, W = xc.shape
+        y = torch.empty_like(xc)
+        N.check(lib, lib.pcd_channel_shuffle(N.ptr(xc), N.ptr(y), B, Cc, H * W, groups, N.stream_for(xc)),
+                "pcd_channel_shuffle")
+        ctx.groups = groups
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = N.lib_for(gy)
+        gy = _f32c(gy)
+        B, Cc, H, W = gy.shape
+        gx = torch.empty_like(gy)
+        # inverse of a (groups, C/groups) transpose is the (C/groups, groups) transpose
+        N.check(lib, lib.pcd_channel_shuffle(N.ptr(gy), N.ptr(gx), B, Cc, H * W, Cc // ctx.groups, N.stream_for(gy)),
+                "pcd_channel_shuffle")
+        return gx, None
+
+
+# --------------------------------------------------------------------------------------------
+# stand-alone preprocess ops (ReLUConvBN 1x1 / FactorizedReduce, affine=False)
+# --------------------------------------------------------------------------------------------
+class PreprocessFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, *weights):
+        fr, c_in, c_out, ptrs = meta
+        lib = N.lib_for(x)
+        xc = _f32c(x)
+        B, _, H, W = xc.shape
+        ho, wo = (H // 2, W // 2) if fr else (H, W)
+        y = torch.empty((B, c_out, ho, wo), dtype=torch.float32, device=xc.device)
+        stats = torch.empty(2 * c_out, dtype=torch.float64, device=xc.device)
+        a = N.PreArgs(B, c_in, c_out, H, W, int(fr), BN_EPS, BN_MOMENTUM, N.ptr(xc), ptrs[0], ptrs[1], ptrs[2],
+                      N.ptr(y), N.ptr(stats), None, None, None, None)
+        N.check(lib, lib.pcd_preprocess_forward(C.byref(a), N.stream_for(xc)), "pcd_preprocess_forward")
+        ctx.meta, ctx.wshapes = (fr, c_in, c_out, ptrs, B, H, W), [w.shape for w in weights]
+        ctx.save_for_backward(xc, y, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, stats = ctx.saved_tensors
+        fr, c_in, c_out, ptrs, B, H, W = ctx.meta
+        lib = N.lib_for(x)
+        gy = _f32c(gy)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        need_w = any(ctx.needs_input_grad[2:])
+        gw = torch.empty(c_out * c_in, dtype=torch.float32, device=x.device) if need_w else None
+        bstats = torch.empty(2 * c_out, dtype=torch.float64, device=x.device)
+        a = N.PreArgs(B, c_in, c_out, H, W, int(fr), BN_EPS, BN_MOMENTUM, N.ptr(x), ptrs[0], None, None, N.ptr(y),
+                      N.ptr(stats), N.ptr(gy), N.ptr(gx), N.ptr(gw), N.ptr(bstats))
+        N.check(lib, lib.pcd_preprocess_backward(C.byref(a), N.stream_for(x)), "pcd_preprocess_backward")
+        if need_w:
+            parts = gw.split_with_sizes([s.numel() for s in ctx.wshapes])
+            gws = [p.view(s) for p, s in zip(parts, ctx.wshapes)]
+        else:
+            gws = [None] * len(ctx.wshapes)
+        return (gx, None, *gws)
+
+
+def preprocess_apply(module, x, fr):
+    """Stand-alone forward of ReLUConvBN(k=1) / FactorizedReduce through the Cell's preprocess kernels."""
+    if fr:
+        c_in, c_out, affine = module._spec
+        bn = module.bn
+    else:
+        c_in, c_out, k, stride, pad, affine = module._spec
+        if (k, stride, pad) != (1, 1, 0):
+            raise NotImplementedError("only the 1x1/stride 1/pad 0 ReLUConvBN of the search network is accelerated")
+        bn = module.op[2]
+    if affine or not module.training:
+        raise NotImplementedError("preprocess kernels implement training-mode BatchNorm with affine=False")
+    if not hasattr(module, "_pcd_arena"):
+        module._pcd_arena = Arena(module)
+    ar = module._pcd_arena.ensure()
+    meta = (fr, c_in, c_out, (ar.param_ptr, ar.running_ptr, ar.nbt_ptr))
+    return PreprocessFunction.apply(x, meta, *ar.params)

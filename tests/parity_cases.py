@@ -1,0 +1,150 @@
+"""Parity cases shared by the CPU-emulation tests and the GPU tests.
+
+Each case builds the product module (lct-vqa_b200/), loads the same seeded weights the golden
+generator gave the reference, runs forward + backward on `device` and compares with the committed
+reference outputs (tests/golden/*.npz) and/or the oracle.  Tolerance: rel 1e-4 (north_star), shuffle /
+partial-channel indexing bit-exact.
+"""
+import torch
+
+from helpers import REL_TOL, assert_close, load_golden, rel_err
+from oracle import pcdarts_oracle as O
+
+MIXED = [("t1", 16, 1), ("t2", 32, 2), ("t3", 32, 1), ("t4", 64, 2), ("t5", 64, 1), ("odd", 16, 1), ("rect2", 16, 2)]
+CELLS = [("normal", 48, 48, 16, False, False), ("reduce", 48, 64, 32, True, False),
+         ("reduce_rp", 64, 128, 64, True, True), ("normal_rp", 128, 256, 64, False, True)]
+
+
+def _fill(module, seed):
+    sd = module.state_dict()
+    O.synth_fill_(sd, seed)
+    module.load_state_dict(sd)
+
+
+def _check_buffers(module, g, tol=1e-5):
+    for k, v in module.state_dict().items():
+        if "running" in k or "tracked" in k:
+            assert_close(v.float(), g["buf." + k].float(), tol, k)
+
+
+def mixed_case(name, C, stride, device):
+    import config
+    config.DEVICE = device
+    from pcdarts.model_search import MixedOp
+    g = load_golden("mixed_" + name)
+    m = MixedOp(C, stride).train()
+    _fill(m, 100 + C + stride)
+    m.to(device)
+    x = g["x"].to(device).requires_grad_(True)
+    w = g["w"].to(device).requires_grad_(True)
+    y = m(x, w)
+    assert_close(y, g["y"], REL_TOL, "y")
+    c = C // 4
+    if stride == 1:      # bypass channels are bit-exact copies: out[:, 4j+q] = x[:, q*c+j]
+        for q in range(1, 4):
+            assert torch.equal(y[:, q::4], x[:, q * c:(q + 1) * c])
+    else:
+        mp = torch.nn.functional.max_pool2d(x[:, c:].detach(), 2, 2)
+        for q in range(1, 4):
+            assert torch.equal(y[:, q::4], mp[:, (q - 1) * c:q * c])
+    _check_buffers(m, g)
+    (y * g["G"].to(device)).sum().backward()
+    assert_close(x.grad, g["dx"], REL_TOL, "dx")
+    assert_close(w.grad, g["dw"], REL_TOL, "dw")
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g["grad." + k], REL_TOL, k)
+
+
+def cell_case(name, cpp, cp, C, red, rp, device):
+    import config
+    config.DEVICE = device
+    from pcdarts.model_search import Cell
+    g = load_golden("cell_" + name)
+    m = Cell(4, 4, cpp, cp, C, red, rp).train()
+    _fill(m, 200 + C + red + 2 * rp)
+    m.to(device)
+    ins = [g[k].to(device).requires_grad_(True) for k in ("s0", "s1", "w", "w2")]
+    y = m(*ins)
+    assert_close(y, g["y"], REL_TOL, "y")
+    _check_buffers(m, g)
+    (y * g["G"].to(device)).sum().backward()
+    for t, k in zip(ins, ("ds0", "ds1", "dw", "dw2")):
+        assert_close(t.grad, g[k], REL_TOL, k)
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g["grad." + k], REL_TOL, k)
+
+
+def network_case(device):
+    import config
+    config.DEVICE = device
+    from pcdarts.model_search import Network
+    g = load_golden("network32")
+    net = Network(16, 10, 4).train()
+    _fill(net, 300)
+    net.to(device)
+    for i, a in enumerate(net.arch_parameters()):
+        a.data.copy_(g[f"arch{i}"])
+    y = net(g["x"].to(device))
+    assert_close(y, g["y"], REL_TOL, "y")
+    (y * g["G"].to(device)).sum().backward()
+    for i, a in enumerate(net.arch_parameters()):
+        assert_close(a.grad, g[f"darch{i}"], REL_TOL, f"darch{i}")
+    named = dict(net.named_parameters())
+    keys = [str(k) for k in g["grad_keys"]]
+    assert keys == list(named.keys()), "parameter registration order differs from the reference"
+    l2 = [named[k].grad.norm().item() for k in keys]
+    for k, a, b in zip(keys, l2, g["grad_l2"].tolist()):
+        assert abs(a - b) <= REL_TOL * max(b, 1e-9), (k, a, b)
+    for k in g:
+        if k.startswith("grad."):
+            assert_close(named[k[5:]].grad, g[k], REL_TOL, k)
+    sd = net.state_dict()
+    bsum = torch.tensor([sd[str(k)].double().sum().item() for k in g["buf_keys"]], dtype=torch.float64)
+    assert_close(bsum, g["buf_sum"], 1e-5, "running stats")
+    return net
+
+
+def shuffle_case(device):
+    from pcdarts.model_search import channel_shuffle
+    g = load_golden("shuffle")
+    x = g["x"].clone().to(device).requires_grad_(True)
+    y = channel_shuffle(x, 4)
+    assert torch.equal(y.cpu(), g["y"])
+    G = torch.randn(y.shape, generator=torch.Generator().manual_seed(0))
+    y.backward(G.to(device))
+    ref = g["x"].detach().clone().requires_grad_(True)
+    O.channel_shuffle(ref).backward(G)
+    assert torch.equal(x.grad.cpu(), ref.grad)
+
+
+def mixed_vs_oracle(C, stride, B, H, device, seed=7, check_grads=True):
+    """Larger shapes than the goldens: product on `device` vs the oracle on CPU, same seeded inputs."""
+    import config
+    config.DEVICE = device
+    from pcdarts.model_search import MixedOp
+    m = MixedOp(C, stride).train()
+    _fill(m, seed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    par, buf = O.split_state(sd)
+    for v in par.values():
+        v.requires_grad_(True)
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, H, generator=gen)
+    w = torch.softmax(torch.randn(8, generator=gen), 0)
+    G = torch.randn(B, C, H // stride, H // stride, generator=gen)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = O.mixed_op(par, O.BNState(buf), "_ops.", xr, wr, stride)
+    (yr * G).sum().backward()
+    m.to(device)
+    xd, wd = x.to(device).requires_grad_(True), w.to(device).requires_grad_(True)
+    y = m(xd, wd)
+    assert_close(y, yr, REL_TOL, "y")
+    (y * G.to(device)).sum().backward()
+    assert_close(xd.grad, xr.grad, REL_TOL, "dx")
+    assert_close(wd.grad, wr.grad, REL_TOL, "dw")
+    if check_grads:
+        for k, p in m.named_parameters():
+            assert_close(p.grad, par[k].grad, REL_TOL, k)
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            assert_close(v, buf[k], 1e-5, k)

@@ -1,0 +1,45 @@
+"""CPU checks of the CUDA kernel SOURCES: the same .cuh bodies compiled with -DPCD_EMU (phases run as
+host loops) against the reference goldens.  This validates index arithmetic / math of the kernels
+where no GPU exists; it is test infrastructure, not a product path (see pcd_native.enable_emulation).
+"""
+import pytest
+import torch
+
+import parity_cases as P
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulation():
+    import pcd_build
+    import pcd_native
+    pcd_native.enable_emulation(pcd_build.build_emu())
+    yield
+    pcd_native._emu_lib = None
+
+
+@pytest.mark.parametrize("name,C,stride", P.MIXED)
+def test_mixed_op_emulated(name, C, stride):
+    P.mixed_case(name, C, stride, "cpu")
+
+
+@pytest.mark.parametrize("name,cpp,cp,C,red,rp", P.CELLS)
+def test_cell_emulated(name, cpp, cp, C, red, rp):
+    P.cell_case(name, cpp, cp, C, red, rp, "cpu")
+
+
+def test_network_emulated():
+    P.network_case("cpu")
+
+
+def test_shuffle_emulated():
+    P.shuffle_case("cpu")
+
+
+def test_product_refuses_cpu_without_emulation():
+    import pcd_native
+    keep, pcd_native._emu_lib = pcd_native._emu_lib, None
+    try:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            pcd_native.lib_for(torch.zeros(1))
+    finally:
+        pcd_native._emu_lib = keep
