@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — search steps/sec of the PC-DARTS-VQA search step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+One "step" = the alpha-step (unrolled, finite-difference Hessian-vector product; --first-order for the
+first-order architect) followed by the w-step of darts_vqa/experiment.py:176-200 on one synthetic batch
+of B=64 per GPU (64x64 images, 30-token questions, V=17858, 1000 answers, C=16, 4 cells).  For N>1 the
+driver launches one rank per GPU with torchrun; the batch is sharded (weak scaling: 64 per GPU) and
+gradients are averaged with NCCL.
+
+Prints ONE JSON line (rank 0).  value = whole-job 64-sample search steps per second with inputs
+resident in HBM; e2e = the same through the public API with host (pinned) inputs copied inside the
+timed region and the loss read back; roofline = MixedOp kernel group measured with per-launch CUDA
+events in a separate profiled region; cpu_baseline = the oracle port on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "lct-vqa_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "search steps/sec (w+alpha step)"
+UNIT = "steps/s"
+DIMS = dict(embed_size=512, ans_vocab_size=1000, word_embed_size=300, num_layers=1, hidden_size=512)
+# algorithmic bytes of all 56 MixedOp edges at B=64 (fwd 1241.5 MB, fwd+bwd 2977.5 MB)
+MIXED_FWD_MB_B64, MIXED_BWD_MB_B64 = 1241.5136, 1736.0
+MIXED_KERNELS = ("passA", "passB", "combine", "node_stats", "bwdB", "bwdA", "SourceGrad", "ArchGrads")
+EDGE_SHAPES = [("T1 C16@64 s1", 16, 1, 64, 14), ("T2 C32 64->32 s2", 32, 2, 64, 8), ("T3 C32@32 s1", 32, 1, 32, 6),
+               ("T4 C64 32->16 s2", 64, 2, 32, 8), ("T5 C64@16 s1", 64, 1, 16, 20)]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (reference default 64)")
+    ap.add_argument("--vocab", type=int, default=17858)
+    ap.add_argument("--img", type=int, default=64)
+    ap.add_argument("--first-order", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+def workload(a, n):
+    return {"workload": f"PC-DARTS-VQA search step: {'first-order' if a.first_order else 'unrolled (HVP)'} alpha-step"
+                        f" + w-step, VqaModel(512,{a.vocab},1000,300,1,512,'darts'), C=16, 4 cells, {a.img}x{a.img}",
+            "batch_per_gpu": a.batch, "global_batch": a.batch * n, "parallelism": f"dp{n}", "unrolled": not a.first_order,
+            "l2": "no flush needed: each pass streams ~1.8 GB of saved activations at B=64 (>> 126 MB L2); "
+                  "the MixedOp micro-benchmark flushes L2 with a 512 MB write between iterations"}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_batch(seed, B, V, img):
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn(B, 3, img, img, generator=g)
+    qst = torch.randint(0, V, (B, 30), generator=g)
+    qst[:, 0] = 2
+    lbl = torch.randint(0, 1000, (B,), generator=g)
+    return image, qst, lbl
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path (oracle/pcdarts_oracle.py)
+# ------------------------------------------------------------------------------------------------------
+def cpu_search_step_factory(a, B):
+    from oracle import pcdarts_oracle as O
+    torch.manual_seed(10)
+    sd = O.alloc_state(O.vqa_spec(qst_vocab_size=a.vocab, **DIMS), seed=10)
+    par, buf = O.split_state(sd)
+    for v in par.values():
+        v.requires_grad_(True)
+    arch = [(1e-3 * torch.randn(s)).requires_grad_(True) for s in ((14, 8), (14, 8), (14,), (14,))]
+    keys = list(par.keys())
+    train, valid = synth_batch(10, B, a.vocab, a.img), synth_batch(11, B, a.vocab, a.img)
+    st_a, st_w, bns = {}, {}, O.BNState(buf)
+
+    def step():
+        O.architect_step(par, bns, arch, st_a, train, valid, 1e-3, keys, unrolled=not a.first_order)
+        return float(O.w_step(par, bns, arch, train, st_w, keys))
+    return step
+
+
+def time_cpu(a, steps, warmup, budget_s):
+    """Time the oracle port on a bounded sample: the per-GPU batch is cut to B_cpu so the run fits the budget."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t0 = time.time()
+    probe = cpu_search_step_factory(a, 1)
+    t1 = time.time()
+    probe()
+    per_sample = time.time() - t1            # one sample, includes first-call overheads
+    B = 1
+    for cand in (2, 4, 8, 16, 32, 64):
+        if cand <= a.batch and per_sample * cand * 0.6 * (steps + warmup) <= budget_s:
+            B = cand
+    step = cpu_search_step_factory(a, B) if B > 1 else probe
+    for _ in range(warmup):
+        step()
+    t = time.time()
+    for _ in range(steps):
+        step()
+    dt = (time.time() - t) / steps
+    value = (1.0 / dt) * (B / a.batch)
+    return value, dt, {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{steps} step(s) (+{warmup} warm-up) of the same search step on {B} of the "
+                                 f"{a.batch} samples of the batch, {dt:.2f} s each; value = steps/s scaled by "
+                                 f"{B}/{a.batch} (cost is linear in the batch); setup {t1 - t0:.1f} s not timed"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, dt, cb = time_cpu(a, a.steps, a.warmup, budget_s=150.0)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload(a, a.gpus), "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch.distributed as dist
+    import config
+    import pcd_dist as pdist
+    import pcd_native
+    from argparse import Namespace
+
+    rank, world = pdist.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    config.DEVICE = dev
+    lib = pcd_native.load_cuda()
+    from pcdarts.architect_vqa import Architect
+    from search import SearchStep
+    from vqa_model import VqaModel
+
+    torch.manual_seed(10)
+    model = VqaModel(qst_vocab_size=a.vocab, img_encoder_type="darts", **DIMS).to(dev).train()
+    reducer = pdist.GradReducer() if world > 1 else None
+    if world > 1:           # identical replicas: rank 0's init everywhere
+        for t in list(model.parameters()) + list(model.buffers()) + list(model.arch_parameters()):
+            dist.broadcast(t.data, 0)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    architect = Architect(model, Namespace(arch_learn_rate=6e-4, arch_wt_decay=1e-3, qst_only=False), reducer=reducer)
+    stepper = SearchStep(model, architect, opt, reducer=reducer)
+    host_train = [t.pin_memory() for t in synth_batch(10 + rank, a.batch, a.vocab, a.img)]
+    host_valid = [t.pin_memory() for t in synth_batch(1010 + rank, a.batch, a.vocab, a.img)]
+    train = [t.to(dev) for t in host_train]
+    valid = [t.to(dev) for t in host_valid]
+    unrolled = not a.first_order
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return ms.item()
+
+    def step_resident():
+        stepper.step(train, valid, 1e-3, unrolled=unrolled)
+
+    def step_e2e():
+        tr = [t.to(dev, non_blocking=True) for t in host_train]
+        va = [t.to(dev, non_blocking=True) for t in host_valid]
+        return stepper.step(tr, va, 1e-3, unrolled=unrolled).item()
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.pcd_launch_count()
+    ms = timed(step_resident, a.steps)
+    launches = lib.pcd_launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = world * a.steps / (ms / 1e3)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    h2d = 2 * sum(t.numel() * t.element_size() for t in host_train)
+    e2e = {"value": world * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "ms_per_step": ms_e2e / a.steps}
+
+    # ---- per-launch CUDA-event profile of this library's kernels (separate region: events perturb) ----
+    hbm, peak_src = peaks()
+    roofline, by_kernel = None, {}
+    if rank == 0:
+        nprof = 2
+        lib.pcd_profile_enable(1)
+        for _ in range(nprof):
+            step_resident()
+        torch.cuda.synchronize()
+        prof = pcd_native.profile_collect(lib)
+        lib.pcd_profile_enable(0)
+        total_ms = sum(v[0] for v in prof.values())
+        for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            by_kernel[k] = {"ms_per_step": t / nprof, "launches_per_step": c / nprof, "share": t / total_ms}
+        mixed_ms = sum(t for k, (t, c) in prof.items() if k.startswith(MIXED_KERNELS)) / nprof
+        n_fwd = 5 if unrolled else 2
+        n_bwd = 5 if unrolled else 2
+        alg_mb = (n_fwd * MIXED_FWD_MB_B64 + n_bwd * MIXED_BWD_MB_B64) * a.batch / 64.0
+        achieved = alg_mb / 1e3 / (mixed_ms / 1e3)
+        top = next(iter(by_kernel))
+        roofline = {"bound": "hbm", "kernel": "MixedOp kernel group (passA,passB,combine | node_stats,bwdB,bwdA,"
+                                              "source_grad,arch_grads): all 56 edges x all passes of one step",
+                    "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                    "algorithmic_mb_per_step": alg_mb, "kernel_ms_per_step": mixed_ms, "peak_source": peak_src,
+                    "passes_per_step": {"forward": n_fwd, "backward": n_bwd},
+                    "dominant_kernel": top, "native_kernel_ms_per_step": total_ms / nprof,
+                    "share_of_step": (total_ms / nprof) / (ms / a.steps), "by_kernel": by_kernel}
+
+    extras = {}
+    if not a.no_extras:
+        extras["mixedop_fwd_bwd"] = mixedop_microbench(dev, a.batch, hbm)
+        if rank == 0 or world > 1:
+            w_ms = timed(lambda: stepper.w_step(*train), max(3, a.steps // 2)) / max(3, a.steps // 2)
+            fo_ms = timed(lambda: stepper.step(train, valid, 1e-3, unrolled=False), max(3, a.steps // 2)) / max(3, a.steps // 2)
+            extras["w_step_only_steps_per_s"] = world * 1e3 / w_ms
+            extras["w_plus_first_order_alpha_steps_per_s"] = world * 1e3 / fo_ms
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        _, _, cpu = time_cpu(a, 1, 0, budget_s=20.0)
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+               "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": workload(a, world), "e2e": e2e, "gpu_launches": int(launches),
+               "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
+               "comm": None if reducer is None else {"allreduce_calls": reducer.calls, "allreduce_bytes": reducer.bytes}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def mixedop_microbench(dev, B, hbm):
+    """MixedOp fwd+bwd at the five production edge shapes, L2 flushed between iterations."""
+    from pcdarts.model_search import MixedOp
+    flush = torch.empty(128 << 20, dtype=torch.float32, device=dev)
+    res = []
+    for name, C, s, H, count in EDGE_SHAPES:
+        m = MixedOp(C, s).to(dev).train()
+        x = torch.randn(B, C, H, H, device=dev, requires_grad=True)
+        w = torch.softmax(torch.randn(8, device=dev), 0).requires_grad_(True)
+        G = torch.randn(B, C, H // s, H // s, device=dev)
+        for _ in range(3):
+            m(x, w).backward(G)
+        tot = 0.0
+        iters = 5
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            m(x, w).backward(G)
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        ms = tot / iters
+        c = C // 4
+        s_in, s_out = B * H * H, B * (H // s) * (H // s)
+        fwd = 4 * C * (s_in + s_out)
+        bwd = 4 * s_in * (2 * C + c) if s == 1 else 4 * (C * s_out + 2 * C * s_in)
+        gbs = (fwd + bwd) / 1e9 / (ms / 1e3)
+        res.append({"shape": name, "edges_per_pass": count, "ms": ms, "algorithmic_mb": (fwd + bwd) / 1e6,
+                    "gb_per_s": gbs, "frac_of_hbm_peak": gbs / hbm})
+    return res
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -47,6 +47,15 @@ const char* pcd_strerror(int status);
 int pcd_is_cuda_build(void);
 const char* pcd_last_cuda_error(void);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched since it was loaded, and an
+ * optional per-launch CUDA-event profiler (events are recorded on the launching stream around every
+ * kernel while enabled; collect() synchronises them and accumulates milliseconds per kernel id). */
+long long pcd_launch_count(void);
+int pcd_profile_enable(int on);
+int pcd_profile_num_kernels(void);
+const char* pcd_profile_kernel_name(int id);
+int pcd_profile_collect(double* ms, long long* count, int max_kernels);
+
 /* ------------------------------------------------------------------------------------------------
  * channel_shuffle(x, groups)                     darts_vqa/pcdarts/model_search.py:14-28
  * out[:, j*groups + g] = in[:, g*(C/groups) + j]   — bit-exact copy.

@@ -13,9 +13,26 @@
 
 namespace pcd {
 
+// ---- launch bookkeeping: a counter (always on) and an optional per-launch CUDA-event profiler ------------
+static long long g_launches = 0;
+constexpr int kMaxKernels = 64, kMaxRecords = 1 << 16;
+static const char* g_kernel_names[kMaxKernels];
+static int g_num_kernels = 0;
+static int g_prof_on = 0, g_prof_n = 0;
+static int g_prof_kid[kMaxRecords];
+
+static int register_kernel(const char* name) {
+    for (int i = 0; i < g_num_kernels; ++i)
+        if (!strcmp(g_kernel_names[i], name)) return i;
+    if (g_num_kernels >= kMaxKernels) return kMaxKernels - 1;
+    g_kernel_names[g_num_kernels] = name;
+    return g_num_kernels++;
+}
+
 #if PCD_CUDA
 #define PCD_D __device__ __forceinline__
 static thread_local char g_last_err[256] = "";
+static cudaEvent_t* g_prof_ev = nullptr;    // 2 events per record, created on first enable
 
 template <class Body, class Args>
 __global__ void __launch_bounds__(kThreads) pcd_kernel(const Args a) {
@@ -40,7 +57,12 @@ static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, voi
             configured = 227 * 1024;
         }
     }
+    static const int kid = register_kernel(Body::name());
+    const int rec = (g_prof_on && g_prof_n < kMaxRecords) ? g_prof_n++ : -1;
+    if (rec >= 0) { g_prof_kid[rec] = kid; cudaEventRecord(g_prof_ev[2 * rec], (cudaStream_t)stream); }
     pcd_kernel<Body, Args><<<dim3(gx, gy, gz), kThreads, bytes, (cudaStream_t)stream>>>(a);
+    if (rec >= 0) cudaEventRecord(g_prof_ev[2 * rec + 1], (cudaStream_t)stream);
+    ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_last_err, sizeof g_last_err, "launch: %s", cudaGetErrorString(e));
@@ -66,6 +88,9 @@ template <class Body, class Args>
 static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, void*) {
     if (gx <= 0 || gy <= 0 || gz <= 0) return PCD_OK;
     if (smem_floats * sizeof(float) > 227 * 1024) return PCD_ERR_UNSUPPORTED;
+    static const int kid = register_kernel(Body::name());
+    (void)kid;
+    ++g_launches;
     float* smem = (float*)aligned_alloc(64, (smem_floats * sizeof(float) + 63) / 64 * 64);
     for (int z = 0; z < gz; ++z)
         for (int y = 0; y < gy; ++y)
@@ -84,23 +109,23 @@ static int zero_async(void* p, size_t bytes, void*) {
 #endif
 
 // ---- kernel body adaptors -----------------------------------------------------------------------------
-template <int C, int S> struct KPassA { static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { passA_body<C, S>(a, x, y, z, sm); } };
-template <int C> struct KPassB { static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { passB_body<C>(a, x, y, z, sm); } };
-template <int C> struct KCombine { static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
-struct KPreConv { static PCD_D void run(const PreArgs& a, int x, int y, int, float* sm) { pre_conv_body(a, x, y, sm); } };
-struct KNorm { static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
-struct KStem { static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
-struct KGapF { static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };
-struct KGapB { static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_bwd_body(a, x); } };
-struct KShuffle { static PCD_D void run(const ShuffleArgs& a, int x, int y, int z, float*) { shuffle_body(a, x, y, z); } };
-template <int C> struct KNodeStats { static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
-template <int C> struct KBwdB { static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdB_body<C>(a, x, y, z, sm); } };
-template <int C, int S> struct KBwdA { static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdA_body<C, S>(a, x, y, z, sm); } };
-struct KSourceGrad { static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
-struct KArchGrads { static PCD_D void run(const ArchGradArgs& a, int, int, int, float*) { arch_grads_body(a); } };
-struct KBnBwdStats { static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
-struct KPreBwd { static PCD_D void run(const PreBwdArgs& a, int x, int, int, float* sm) { pre_bwd_body(a, x, a.nblocks_launch, sm); } };
-struct KStemBwd { static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd_body(a, x, a.nblocks_launch, sm); } };
+template <int C, int S> struct KPassA { static const char* name() { return S == 1 ? (C == 4 ? "passA_c4_s1" : C == 8 ? "passA_c8_s1" : "passA_c16_s1") : (C == 4 ? "passA_c4_s2" : C == 8 ? "passA_c8_s2" : "passA_c16_s2"); } static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { passA_body<C, S>(a, x, y, z, sm); } };
+template <int C> struct KPassB { static const char* name() { return C == 4 ? "passB_c4" : C == 8 ? "passB_c8" : "passB_c16"; } static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { passB_body<C>(a, x, y, z, sm); } };
+template <int C> struct KCombine { static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
+struct KPreConv { static const char* name() { return "PreConv"; } static PCD_D void run(const PreArgs& a, int x, int y, int, float* sm) { pre_conv_body(a, x, y, sm); } };
+struct KNorm { static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
+struct KStem { static const char* name() { return "Stem"; } static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
+struct KGapF { static const char* name() { return "GapF"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };
+struct KGapB { static const char* name() { return "GapB"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_bwd_body(a, x); } };
+struct KShuffle { static const char* name() { return "Shuffle"; } static PCD_D void run(const ShuffleArgs& a, int x, int y, int z, float*) { shuffle_body(a, x, y, z); } };
+template <int C> struct KNodeStats { static const char* name() { return C == 4 ? "node_stats_c4" : C == 8 ? "node_stats_c8" : "node_stats_c16"; } static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
+template <int C> struct KBwdB { static const char* name() { return C == 4 ? "bwdB_c4" : C == 8 ? "bwdB_c8" : "bwdB_c16"; } static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdB_body<C>(a, x, y, z, sm); } };
+template <int C, int S> struct KBwdA { static const char* name() { return S == 1 ? (C == 4 ? "bwdA_c4_s1" : C == 8 ? "bwdA_c8_s1" : "bwdA_c16_s1") : (C == 4 ? "bwdA_c4_s2" : C == 8 ? "bwdA_c8_s2" : "bwdA_c16_s2"); } static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdA_body<C, S>(a, x, y, z, sm); } };
+struct KSourceGrad { static const char* name() { return "SourceGrad"; } static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
+struct KArchGrads { static const char* name() { return "ArchGrads"; } static PCD_D void run(const ArchGradArgs& a, int, int, int, float*) { arch_grads_body(a); } };
+struct KBnBwdStats { static const char* name() { return "BnBwdStats"; } static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
+struct KPreBwd { static const char* name() { return "PreBwd"; } static PCD_D void run(const PreBwdArgs& a, int x, int, int, float* sm) { pre_bwd_body(a, x, a.nblocks_launch, sm); } };
+struct KStemBwd { static const char* name() { return "StemBwd"; } static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd_body(a, x, a.nblocks_launch, sm); } };
 
 #define PCD_DISPATCH_C(c, EXPR)                         \
     do {                                                \
@@ -305,6 +330,40 @@ using namespace pcd;
 extern "C" {
 
 int pcd_version(void) { return PCD_VERSION; }
+long long pcd_launch_count(void) { return g_launches; }
+
+int pcd_profile_enable(int on) {
+#if PCD_CUDA
+    if (on && !g_prof_ev) {
+        g_prof_ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * 2 * kMaxRecords);
+        for (int i = 0; i < 2 * kMaxRecords; ++i)
+            if (cudaEventCreate(&g_prof_ev[i]) != cudaSuccess) return PCD_ERR_CUDA;
+    }
+#endif
+    if (on) g_prof_n = 0;
+    g_prof_on = on;
+    return PCD_OK;
+}
+
+int pcd_profile_num_kernels(void) { return g_num_kernels; }
+const char* pcd_profile_kernel_name(int id) { return (id >= 0 && id < g_num_kernels) ? g_kernel_names[id] : ""; }
+
+/* Synchronises the recorded events; adds each launch's duration to ms[kernel id] and bumps count[kernel id]. */
+int pcd_profile_collect(double* ms, long long* count, int max_kernels) {
+    if (!ms || !count) return PCD_ERR_ARG;
+#if PCD_CUDA
+    for (int r = 0; r < g_prof_n; ++r) {
+        float t = 0.f;
+        if (cudaEventSynchronize(g_prof_ev[2 * r + 1]) != cudaSuccess) return PCD_ERR_CUDA;
+        if (cudaEventElapsedTime(&t, g_prof_ev[2 * r], g_prof_ev[2 * r + 1]) != cudaSuccess) return PCD_ERR_CUDA;
+        const int k = g_prof_kid[r];
+        if (k < max_kernels) { ms[k] += t; count[k] += 1; }
+    }
+#endif
+    const int n = g_prof_n;
+    g_prof_n = 0;
+    return n;
+}
 int pcd_is_cuda_build(void) { return PCD_CUDA; }
 const char* pcd_last_cuda_error(void) { return g_last_err; }
 const char* pcd_strerror(int s) {

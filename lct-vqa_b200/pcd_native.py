@@ -74,7 +74,8 @@ class PreArgs(C.Structure):
                     "x", "weight", "running", "nbt", "y", "stats", "grad_y", "grad_x", "grad_weight", "bstats")]
 
 
-EXPORTS = ("pcd_version", "pcd_strerror", "pcd_is_cuda_build", "pcd_last_cuda_error", "pcd_channel_shuffle",
+EXPORTS = ("pcd_launch_count", "pcd_profile_enable", "pcd_profile_num_kernels", "pcd_profile_kernel_name",
+           "pcd_profile_collect", "pcd_version", "pcd_strerror", "pcd_is_cuda_build", "pcd_last_cuda_error", "pcd_channel_shuffle",
            "pcd_cell_sizes_of", "pcd_cell_forward", "pcd_cell_backward", "pcd_mixedop_sizes_of",
            "pcd_mixedop_forward", "pcd_mixedop_backward", "pcd_stem_forward", "pcd_stem_backward",
            "pcd_preprocess_forward", "pcd_preprocess_backward", "pcd_adaptive_avgpool_forward", "pcd_adaptive_avgpool_backward")
@@ -86,6 +87,10 @@ def _declare(lib):
     lib.pcd_strerror.restype = C.c_char_p
     lib.pcd_strerror.argtypes = [C.c_int]
     lib.pcd_last_cuda_error.restype = C.c_char_p
+    lib.pcd_launch_count.restype = C.c_longlong
+    lib.pcd_profile_kernel_name.restype = C.c_char_p
+    lib.pcd_profile_kernel_name.argtypes = [C.c_int]
+    lib.pcd_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
     lib.pcd_channel_shuffle.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.pcd_cell_sizes_of.argtypes = [C.POINTER(CellShape), C.POINTER(CellSizes)]
     lib.pcd_cell_forward.argtypes = [C.POINTER(CellFwdArgs), vp]
@@ -151,3 +156,15 @@ def check(lib, rc, what):
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def profile_collect(lib):
+    """-> {kernel name: (total ms, launches)} for the launches recorded since pcd_profile_enable(1)."""
+    n = 64
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    rc = lib.pcd_profile_collect(ms, cnt, n)
+    if rc < 0:
+        check(lib, rc, "pcd_profile_collect")
+    return {lib.pcd_profile_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(lib.pcd_profile_num_kernels())
+            if cnt[i]}

@@ -1,0 +1,133 @@
+"""Second-order DARTS architect — B200 drop-in for darts_vqa/pcdarts/architect_vqa.py.
+
+Same public surface: Architect(model, args).step(img_train, qst_train, label_train, img_valid,
+qst_valid, label_valid, eta, network_optimizer=None, unrolled=True) with args.arch_learn_rate /
+arch_wt_decay / qst_only; Adam(betas=(0.5, 0.999)) over model.arch_parameters(); the virtual step uses
+momentum = weight decay = 0 and the finite-difference Hessian-vector product uses r = 1e-2
+(architect_vqa.py:15-16,19-21,105).
+
+Same arithmetic, different mechanics:
+  * the unrolled model w' = w - eta * dL_train/dw is a PERSISTENT twin (built once with model.new())
+    whose weights / BN buffers / alphas are overwritten in place with multi-tensor ops, instead of
+    constructing and load_state_dict-ing a fresh 732-tensor model every step (:90-103);
+  * w +- R v and ||v|| are multi-tensor (foreach) kernels over the parameter list, not 732 Python-level
+    in-place ops (:106-118);
+  * the two HVP backward passes only ask autograd for the alpha/beta grads, which switches the CUDA cell
+    kernels to their activation-only mode (no weight-gradient work);
+  * an optional `reducer` averages gradients across data-parallel ranks at the four points where the
+    reference's single-process quantities become global sums.
+"""
+import torch
+
+
+def _concat(xs):
+    return torch.cat([x.reshape(-1) for x in xs])
+
+
+class Architect(object):
+
+    def __init__(self, model, args, reducer=None):
+        self.network_momentum = 0
+        self.network_weight_decay = 0
+        self.model = model
+        self.args = args
+        self.reducer = reducer
+        self.optimizer = torch.optim.Adam(self.model.arch_parameters(), lr=args.arch_learn_rate,
+                                          betas=(0.5, 0.999), weight_decay=args.arch_wt_decay)
+        self.exp_zero_grad = 6 if self.args.qst_only else 0
+        self._twin = None
+        self.last = {}            # quantities of the last unrolled step, for inspection / tests
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    def _allreduce(self, tensors):
+        if self.reducer is not None:
+            self.reducer(tensors)
+
+    def unrolled_model(self):
+        """The persistent twin that holds w' (created on first use through model.new())."""
+        if self._twin is None:
+            self._twin = self.model.new()
+            self._twin.train()
+        return self._twin
+
+    def _calc_grad(self, loss, params, exp_zero_grad=0):
+        grads = list(torch.autograd.grad(loss, params, allow_unused=True))
+        missing = 0
+        for i, p in enumerate(params):
+            if grads[i] is None:
+                grads[i] = torch.zeros_like(p)
+                missing += 1
+        assert missing == exp_zero_grad, (missing, exp_zero_grad)
+        return grads
+
+    # ---- public ------------------------------------------------------------------------------------
+    def step(self, img_train, qst_train, label_train, img_valid, qst_valid, label_valid, eta,
+             network_optimizer=None, unrolled=True):
+        self.optimizer.zero_grad()
+        if unrolled:
+            self._backward_step_unrolled(img_train, qst_train, label_train, img_valid, qst_valid, label_valid,
+                                         eta, network_optimizer)
+        else:
+            self._backward_step(img_valid, qst_valid, label_valid)
+        self.optimizer.step()
+
+    def _backward_step(self, img_valid, qst_valid, label_valid):
+        # first-order: d L_val / d alpha at the current weights (architect_vqa.py:53-55)
+        arch = self.model.arch_parameters()
+        loss = self.model._loss(img_valid, qst_valid, label_valid)
+        grads = torch.autograd.grad(loss, arch)
+        self._allreduce(list(grads))
+        for a, g in zip(arch, grads):
+            a.grad = g
+
+    def _compute_unrolled_model(self, img, qst, label, eta, network_optimizer):
+        model = self.model
+        params = list(model.parameters())
+        loss = model._loss(img, qst, label, self.args.qst_only)
+        grads = self._calc_grad(loss, params, self.exp_zero_grad)
+        self._allreduce(grads)
+        twin = self.unrolled_model()
+        with torch.no_grad():
+            tparams = list(twin.parameters())
+            torch._foreach_copy_(tparams, params)
+            torch._foreach_add_(tparams, grads, alpha=-eta)              # theta - eta * (0 + dtheta)
+            tb, mb = list(twin.buffers()), list(model.buffers())
+            torch._foreach_copy_(tb, mb)                                 # model_dict carries the live BN buffers
+            for x, y in zip(twin.arch_parameters(), model.arch_parameters()):
+                x.copy_(y)
+        return twin
+
+    def _backward_step_unrolled(self, img_train, qst_train, label_train, img_valid, qst_valid, label_valid,
+                                eta, network_optimizer):
+        twin = self._compute_unrolled_model(img_train, qst_train, label_train, eta, network_optimizer)
+        tparams = list(twin.parameters())
+        tarch = twin.arch_parameters()
+        unrolled_loss = twin._loss(img_valid, qst_valid, label_valid, self.args.qst_only)
+        got = torch.autograd.grad(unrolled_loss, list(tarch) + tparams, allow_unused=True)
+        dalpha = [g.clone() for g in got[:len(tarch)]]
+        vector = [torch.zeros_like(p) if g is None else g for g, p in zip(got[len(tarch):], tparams)]
+        self._allreduce(dalpha + vector)
+        implicit = self._hessian_vector_product(vector, img_train, qst_train, label_train)
+        with torch.no_grad():
+            torch._foreach_add_(dalpha, implicit, alpha=-eta)
+        for a, g in zip(self.model.arch_parameters(), dalpha):
+            a.grad = g
+        self.last.update(unrolled_loss=unrolled_loss.detach())
+
+    def _hessian_vector_product(self, vector, img, qst, label, r=1e-2):
+        model = self.model
+        params = list(model.parameters())
+        arch = model.arch_parameters()
+        with torch.no_grad():
+            vnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(vector)))
+            R = (r / vnorm).item()
+            torch._foreach_add_(params, vector, alpha=R)
+        grads_p = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
+        with torch.no_grad():
+            torch._foreach_add_(params, vector, alpha=-2 * R)
+        grads_n = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
+        with torch.no_grad():
+            torch._foreach_add_(params, vector, alpha=R)
+        self._allreduce(grads_p + grads_n)
+        self.last.update(g_pos=grads_p, g_neg=grads_n, R=R, vnorm=vnorm)
+        return [(x - y).div_(2 * R) for x, y in zip(grads_p, grads_n)]

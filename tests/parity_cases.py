@@ -148,3 +148,108 @@ def mixed_vs_oracle(C, stride, B, H, device, seed=7, check_grads=True):
     for k, v in m.state_dict().items():
         if "running" in k:
             assert_close(v, buf[k], 1e-5, k)
+
+
+# ---- whole VQA model, architect, w-step (goldens: tests/golden/make_golden.py) ------------------------
+VQA_DIMS = dict(embed_size=16, qst_vocab_size=40, ans_vocab_size=12, word_embed_size=10, num_layers=1,
+                hidden_size=16)
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def vqa_batch(seed, device, B=2, H=32):
+    g = _gen(seed)
+    img = torch.randn(B, 3, H, H, generator=g)
+    qst = torch.randint(0, VQA_DIMS["qst_vocab_size"], (B, 30), generator=g)
+    qst[:, 0] = 2
+    lbl = torch.randint(0, VQA_DIMS["ans_vocab_size"], (B,), generator=g)
+    return img.to(device), qst.to(device), lbl.to(device)
+
+
+def make_vqa(device, seed=400):
+    import config
+    config.DEVICE = device
+    from vqa_model import VqaModel
+    m = VqaModel(img_encoder_type="darts", **VQA_DIMS).train()
+    _fill(m, seed)
+    m.to(device)
+    for i, a in enumerate(m.arch_parameters()):
+        a.data.copy_(0.5 * torch.randn(a.shape, generator=_gen(30 + i)))
+    m.dropout.p = 0.0
+    return m
+
+
+def vqa_case(device):
+    g = load_golden("vqa")
+    m = make_vqa(device)
+    img, qst, lbl = vqa_batch(11, device)
+    ans, qout = m(img, qst)
+    assert_close(ans, g["ans"], REL_TOL, "ans")
+    assert_close(qout, g["qout"], REL_TOL, "qout")
+    loss = m._loss(img, qst, lbl)
+    assert_close(loss, g["loss"], REL_TOL, "loss")
+    loss.backward()
+    for i, a in enumerate(m.arch_parameters()):
+        assert_close(a.grad, g[f"darch{i}"], REL_TOL, f"darch{i}")
+    named = dict(m.named_parameters())
+    keys = [str(k) for k in g["grad_keys"]]
+    assert keys == list(named.keys()), "parameter registration order differs from the reference"
+    for k, b in zip(keys, g["grad_l2"].tolist()):
+        a = named[k].grad.norm().item()
+        assert abs(a - b) <= REL_TOL * max(b, 1e-9), (k, a, b)
+    for k in g:
+        if k.startswith("grad."):
+            assert_close(named[k[5:]].grad, g[k], REL_TOL, k)
+
+
+def architect_case(device, unrolled):
+    from argparse import Namespace
+    from pcdarts.architect_vqa import Architect
+    g = load_golden("architect_unrolled" if unrolled else "architect_first")
+    m = make_vqa(device)
+    arch = Architect(m, Namespace(arch_learn_rate=6e-4, arch_wt_decay=1e-3, qst_only=False))
+    if unrolled:
+        arch.unrolled_model().dropout.p = 0.0
+    arch.step(*vqa_batch(12, device), *vqa_batch(13, device), 1e-3, None, unrolled=unrolled)
+    for i, a in enumerate(m.arch_parameters()):
+        assert_close(a.grad, g[f"darch{i}"], REL_TOL, f"darch{i}")
+        assert_close(a.detach(), g[f"arch_after{i}"], 1e-5, f"arch_after{i}")
+    sd = m.state_dict()
+    if unrolled:
+        assert_close(arch.last["vnorm"], g["vnorm"], REL_TOL, "|vector|")
+        R = arch.last["R"]
+        scale = max(float(t.abs().max()) for t in arch.last["g_pos"]) / (2 * R)
+        for i in range(4):     # raw finite difference: only the cancellation-aware bound of SURVEY App. C holds
+            hv = (arch.last["g_pos"][i] - arch.last["g_neg"][i]) / (2 * R)
+            assert (hv.cpu() - g[f"hvp{i}"]).abs().max().item() <= 2e-4 * scale
+        assert int(sd["img_encoder.darts.stem.1.num_batches_tracked"]) == 3
+    for k in g["rm_keys"]:
+        assert_close(sd[str(k)], g["buf." + str(k)], 1e-5, str(k))
+
+
+def wstep_case(device):
+    """darts_vqa/experiment.py:187-200: zero_grad, fwd, CE+CE, backward, clip_grad_norm_(5), Adam(1e-3)."""
+    g = load_golden("wstep")
+    m = make_vqa(device)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    crit = torch.nn.CrossEntropyLoss()
+    img, qst, lbl = vqa_batch(14, device)
+    losses = []
+    for _ in range(2):
+        opt.zero_grad()
+        ans, qout = m(img, qst)
+        loss = crit(ans, lbl) + crit(qout[:, :-1].flatten(end_dim=1), qst[:, 1:].flatten())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 5)
+        opt.step()
+        losses.append(loss.item())
+    assert_close(torch.tensor(losses, dtype=torch.float64), torch.as_tensor(g["losses"]), REL_TOL, "losses")
+    named = dict(m.named_parameters())
+    for k, b in zip([str(k) for k in g["keys"]], g["param_l2"].tolist()):
+        a = named[k].norm().item()
+        assert abs(a - b) <= REL_TOL * max(b, 1e-9), (k, a, b)
+    for k in g:
+        if k.startswith("param."):
+            assert_close(named[k[6:]].detach(), g[k], REL_TOL, k)

@@ -35,6 +35,19 @@ def test_shuffle_emulated():
     P.shuffle_case("cpu")
 
 
+def test_vqa_model_emulated():
+    P.vqa_case("cpu")
+
+
+@pytest.mark.parametrize("unrolled", [False, True])
+def test_architect_emulated(unrolled):
+    P.architect_case("cpu", unrolled)
+
+
+def test_w_step_emulated():
+    P.wstep_case("cpu")
+
+
 def test_product_refuses_cpu_without_emulation():
     import pcd_native
     keep, pcd_native._emu_lib = pcd_native._emu_lib, None

@@ -33,6 +33,19 @@ def test_mixed_op_production_shapes_vs_oracle(C, stride, B, H):
     P.mixed_vs_oracle(C, stride, B, H, DEV)
 
 
+def test_vqa_model_golden():
+    P.vqa_case(DEV)
+
+
+@pytest.mark.parametrize("unrolled", [False, True])
+def test_architect_step_golden(unrolled):
+    P.architect_case(DEV, unrolled)
+
+
+def test_w_step_golden():
+    P.wstep_case(DEV)
+
+
 def test_native_library_is_the_one_running():
     import pcd_native
     lib = pcd_native.load_cuda()
