@@ -1,116 +1,43 @@
 // pcd_api.cu — launch orchestration and the extern "C" surface declared in include/pcdarts_sm100.h.
 //
-// Built by nvcc (-gencode arch=compute_100a,code=sm_100a) into libpcdarts_sm100.so.  The same file is
-// compiled by g++ with -DPCD_EMU into tests/emu/libpcd_emu.so, where every kernel body runs as nested
-// host loops over (block, task): test infrastructure for the index arithmetic, never a product path
-// (pcd_is_cuda_build() returns 0 there and the product loader refuses it).
-#include "../../include/pcdarts_sm100.h"
+// Built by nvcc (-gencode arch=compute_100a,code=sm_100a) together with pcd_k_*.cu into
+// libpcdarts_sm100.so.  The same sources are compiled by g++ with -DPCD_EMU into tests/emu/libpcd_emu.so,
+// where every kernel body runs as nested host loops over (block, task): test infrastructure for the index
+// arithmetic, never a product path (pcd_is_cuda_build() returns 0 there and the product loader refuses it).
 #include "pcd_bwd.cuh"
-
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
+#include "pcd_kernels.h"
+#include "pcd_launch.cuh"
 
 namespace pcd {
 
-// ---- launch bookkeeping: a counter (always on) and an optional per-launch CUDA-event profiler ------------
-static long long g_launches = 0;
-constexpr int kMaxKernels = 64, kMaxRecords = 1 << 16;
-static const char* g_kernel_names[kMaxKernels];
-static int g_num_kernels = 0;
-static int g_prof_on = 0, g_prof_n = 0;
-static int g_prof_kid[kMaxRecords];
+static LaunchState g_state;
+LaunchState& launch_state() { return g_state; }
 
-static int register_kernel(const char* name) {
-    for (int i = 0; i < g_num_kernels; ++i)
-        if (!strcmp(g_kernel_names[i], name)) return i;
-    if (g_num_kernels >= kMaxKernels) return kMaxKernels - 1;
-    g_kernel_names[g_num_kernels] = name;
-    return g_num_kernels++;
-}
-
-#if PCD_CUDA
-#define PCD_D __device__ __forceinline__
-static thread_local char g_last_err[256] = "";
-static cudaEvent_t* g_prof_ev = nullptr;    // 2 events per record, created on first enable
-
-template <class Body, class Args>
-__global__ void __launch_bounds__(kThreads) pcd_kernel(const Args a) {
-    extern __shared__ F4 pcd_smem4[];
-    Body::run(a, blockIdx.x, blockIdx.y, blockIdx.z, reinterpret_cast<float*>(pcd_smem4));
-}
-
-template <class Body, class Args>
-static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, void* stream) {
-    const size_t bytes = smem_floats * sizeof(float);
-    if (gx <= 0 || gy <= 0 || gz <= 0) return PCD_OK;
-    if (bytes > 227 * 1024) return PCD_ERR_UNSUPPORTED;
-    if (bytes > 48 * 1024) {
-        static thread_local size_t configured = 0;   // per (Body,Args) instantiation
-        if (bytes > configured) {
-            cudaError_t e = cudaFuncSetAttribute(pcd_kernel<Body, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 227 * 1024);
-            if (e != cudaSuccess) {
-                snprintf(g_last_err, sizeof g_last_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-                return PCD_ERR_CUDA;
-            }
-            configured = 227 * 1024;
-        }
-    }
-    static const int kid = register_kernel(Body::name());
-    const int rec = (g_prof_on && g_prof_n < kMaxRecords) ? g_prof_n++ : -1;
-    if (rec >= 0) { g_prof_kid[rec] = kid; cudaEventRecord(g_prof_ev[2 * rec], (cudaStream_t)stream); }
-    pcd_kernel<Body, Args><<<dim3(gx, gy, gz), kThreads, bytes, (cudaStream_t)stream>>>(a);
-    if (rec >= 0) cudaEventRecord(g_prof_ev[2 * rec + 1], (cudaStream_t)stream);
-    ++g_launches;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        snprintf(g_last_err, sizeof g_last_err, "launch: %s", cudaGetErrorString(e));
-        return PCD_ERR_CUDA;
-    }
-    return PCD_OK;
+int register_kernel(const char* name) {
+    LaunchState& L = g_state;
+    for (int i = 0; i < L.num_kernels; ++i)
+        if (!strcmp(L.names[i], name)) return i;
+    if (L.num_kernels >= kMaxKernels) return kMaxKernels - 1;
+    L.names[L.num_kernels] = name;
+    return L.num_kernels++;
 }
 
 static int zero_async(void* p, size_t bytes, void* stream) {
     if (!bytes) return PCD_OK;
+#if PCD_CUDA
     cudaError_t e = cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream);
     if (e != cudaSuccess) {
-        snprintf(g_last_err, sizeof g_last_err, "memset: %s", cudaGetErrorString(e));
+        snprintf(g_state.last_err, sizeof g_state.last_err, "memset: %s", cudaGetErrorString(e));
         return PCD_ERR_CUDA;
     }
-    return PCD_OK;
-}
 #else
-#define PCD_D inline
-static char g_last_err[256] = "";
-
-template <class Body, class Args>
-static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, void*) {
-    if (gx <= 0 || gy <= 0 || gz <= 0) return PCD_OK;
-    if (smem_floats * sizeof(float) > 227 * 1024) return PCD_ERR_UNSUPPORTED;
-    static const int kid = register_kernel(Body::name());
-    (void)kid;
-    ++g_launches;
-    float* smem = (float*)aligned_alloc(64, (smem_floats * sizeof(float) + 63) / 64 * 64);
-    for (int z = 0; z < gz; ++z)
-        for (int y = 0; y < gy; ++y)
-            for (int x = 0; x < gx; ++x) {
-                for (size_t i = 0; i < smem_floats; ++i) smem[i] = NAN;   // catch reads of unwritten smem
-                Body::run(a, x, y, z, smem);
-            }
-    free(smem);
-    return PCD_OK;
-}
-
-static int zero_async(void* p, size_t bytes, void*) {
+    (void)stream;
     memset(p, 0, bytes);
+#endif
     return PCD_OK;
 }
-#endif
 
 // ---- kernel body adaptors -----------------------------------------------------------------------------
-template <int C, int S> struct KPassA { static const char* name() { return S == 1 ? (C == 4 ? "passA_c4_s1" : C == 8 ? "passA_c8_s1" : "passA_c16_s1") : (C == 4 ? "passA_c4_s2" : C == 8 ? "passA_c8_s2" : "passA_c16_s2"); } static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { passA_body<C, S>(a, x, y, z, sm); } };
-template <int C> struct KPassB { static const char* name() { return C == 4 ? "passB_c4" : C == 8 ? "passB_c8" : "passB_c16"; } static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { passB_body<C>(a, x, y, z, sm); } };
 template <int C> struct KCombine { static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
 struct KPreConv { static const char* name() { return "PreConv"; } static PCD_D void run(const PreArgs& a, int x, int y, int, float* sm) { pre_conv_body(a, x, y, sm); } };
 struct KNorm { static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
@@ -119,8 +46,6 @@ struct KGapF { static const char* name() { return "GapF"; } static PCD_D void ru
 struct KGapB { static const char* name() { return "GapB"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_bwd_body(a, x); } };
 struct KShuffle { static const char* name() { return "Shuffle"; } static PCD_D void run(const ShuffleArgs& a, int x, int y, int z, float*) { shuffle_body(a, x, y, z); } };
 template <int C> struct KNodeStats { static const char* name() { return C == 4 ? "node_stats_c4" : C == 8 ? "node_stats_c8" : "node_stats_c16"; } static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
-template <int C> struct KBwdB { static const char* name() { return C == 4 ? "bwdB_c4" : C == 8 ? "bwdB_c8" : "bwdB_c16"; } static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdB_body<C>(a, x, y, z, sm); } };
-template <int C, int S> struct KBwdA { static const char* name() { return S == 1 ? (C == 4 ? "bwdA_c4_s1" : C == 8 ? "bwdA_c8_s1" : "bwdA_c16_s1") : (C == 4 ? "bwdA_c4_s2" : C == 8 ? "bwdA_c8_s2" : "bwdA_c16_s2"); } static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdA_body<C, S>(a, x, y, z, sm); } };
 struct KSourceGrad { static const char* name() { return "SourceGrad"; } static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
 struct KArchGrads { static const char* name() { return "ArchGrads"; } static PCD_D void run(const ArchGradArgs& a, int, int, int, float*) { arch_grads_body(a); } };
 struct KBnBwdStats { static const char* name() { return "BnBwdStats"; } static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
@@ -135,13 +60,19 @@ struct KStemBwd { static const char* name() { return "StemBwd"; } static PCD_D v
         else return PCD_ERR_UNSUPPORTED;                \
     } while (0)
 
-#define PCD_TRY(x) do { int rc_ = (x); if (rc_ != PCD_OK) return rc_; } while (0)
-
 // ---- geometry of one homogeneous group of edges ---------------------------------------------------------
 struct EdgeGeom {
     int B, c, S, Hs, Ws, Ho, Wo;
     long long nslot() const { return (long long)B * c * Ho * Wo; }
 };
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+// preconditions of the compile-time-tile ("FAST") specialisations: the tile picked for this geometry is one of
+// the fixed ones, tiles are full, every row of every tensor touched starts 16-byte aligned
+static bool fast_ok(const EdgeGeom& q, const Tile& t, bool stageB) {
+    return edge_tile_is_fixed(q.c, q.S, t.TH, t.TW, stageB) && q.Ho % t.TH == 0 && q.Wo % t.TW == 0 && q.Ws % 4 == 0;
+}
 
 static int run_passAB(const EdgeGeom& q, const EdgeF* edges, int n, float eps, void* stream) {
     if (n == 0) return PCD_OK;
@@ -149,17 +80,17 @@ static int run_passAB(const EdgeGeom& q, const EdgeF* edges, int n, float eps, v
     PassArgs a;
     memset(&a, 0, sizeof a);
     a.B = q.B; a.Hs = q.Hs; a.Ws = q.Ws; a.Ho = q.Ho; a.Wo = q.Wo; a.S = q.S; a.eps = eps; a.nedges = n;
-    for (int i = 0; i < n; ++i) a.e[i] = edges[i];
+    bool al = true;
+    for (int i = 0; i < n; ++i) {
+        a.e[i] = edges[i];
+        al = al && aligned16(edges[i].x) && aligned16(edges[i].saved) && edges[i].x_ns % 4 == 0;
+    }
     Tile t = pick_tile(q.Ho, q.Wo, q.c, q.S == 1 ? 4096 : 2048);
     a.TH = t.TH; a.TW = t.TW; a.tiles_x = t.tiles_x;
-    const int tiles = t.tiles_x * t.tiles_y;
-    if (q.S == 1)
-        PCD_DISPATCH_C(q.c, PCD_TRY((launch<KPassA<CC, 1>, PassArgs>(a, tiles, q.B, n, passA_smem_floats(CC, 1, t.TH, t.TW), stream))));
-    else
-        PCD_DISPATCH_C(q.c, PCD_TRY((launch<KPassA<CC, 2>, PassArgs>(a, tiles, q.B, n, passA_smem_floats(CC, 2, t.TH, t.TW), stream))));
+    PCD_TRY(launch_fwdA(a, q.c, al && fast_ok(q, t, false), t.tiles_x * t.tiles_y, q.B, n * kFwdAJobs, stream));
     Tile tb = pick_tile(q.Ho, q.Wo, q.c, 4096);
     a.TH = tb.TH; a.TW = tb.TW; a.tiles_x = tb.tiles_x;
-    PCD_DISPATCH_C(q.c, PCD_TRY((launch<KPassB<CC>, PassArgs>(a, tb.tiles_x * tb.tiles_y, q.B, n, passB_smem_floats(CC, tb.TH, tb.TW), stream))));
+    PCD_TRY(launch_fwdB(a, q.c, al && fast_ok(q, tb, true), tb.tiles_x * tb.tiles_y, q.B, n * 2, stream));
     return PCD_OK;
 }
 
@@ -194,17 +125,18 @@ static int run_edge_bwd(const EdgeGeom& q, const EdgeG* edges, int n, float eps,
     memset(&a, 0, sizeof a);
     a.B = q.B; a.Hs = q.Hs; a.Ws = q.Ws; a.Ho = q.Ho; a.Wo = q.Wo; a.S = q.S; a.eps = eps; a.nedges = n;
     a.need_wgrad = need_wgrad;
-    for (int i = 0; i < n; ++i) a.e[i] = edges[i];
+    bool al = true;
+    for (int i = 0; i < n; ++i) {
+        a.e[i] = edges[i];
+        al = al && aligned16(edges[i].x) && aligned16(edges[i].saved) && aligned16(edges[i].dn) && aligned16(edges[i].ga) &&
+             aligned16(edges[i].pd) && edges[i].x_ns % 4 == 0 && edges[i].dn_ns % 4 == 0;
+    }
     Tile tb = pick_tile(q.Ho, q.Wo, q.c, 4096);
     a.TH = tb.TH; a.TW = tb.TW; a.tiles_x = tb.tiles_x;
-    PCD_DISPATCH_C(q.c, PCD_TRY((launch<KBwdB<CC>, EdgeBwdArgs>(a, tb.tiles_x * tb.tiles_y, q.B, n, bwdB_smem_floats(CC, tb.TH, tb.TW), stream))));
+    PCD_TRY(launch_bwdB(a, q.c, al && fast_ok(q, tb, true), tb.tiles_x * tb.tiles_y, q.B, n * 2, stream));
     Tile t = pick_tile(q.Ho, q.Wo, q.c, q.S == 1 ? 4096 : 2048);
     a.TH = t.TH; a.TW = t.TW; a.tiles_x = t.tiles_x;
-    const int tiles = t.tiles_x * t.tiles_y;
-    if (q.S == 1)
-        PCD_DISPATCH_C(q.c, PCD_TRY((launch<KBwdA<CC, 1>, EdgeBwdArgs>(a, tiles, q.B, n, bwdA_smem_floats(CC, 1, t.TH, t.TW), stream))));
-    else
-        PCD_DISPATCH_C(q.c, PCD_TRY((launch<KBwdA<CC, 2>, EdgeBwdArgs>(a, tiles, q.B, n, bwdA_smem_floats(CC, 2, t.TH, t.TW), stream))));
+    PCD_TRY(launch_bwdA(a, q.c, al && fast_ok(q, t, false), t.tiles_x * t.tiles_y, q.B, n * bwdA_njobs(q.S), stream));
     return PCD_OK;
 }
 
@@ -302,7 +234,7 @@ static int cell_layout(const pcd_cell_shape& s, CellLayout& L) {
             L.bstats[e] = bst; bst += edge_bstats_doubles(c);
             L.saved[e] = sv; sv += edge_nslots(sd) * nslot;
             L.ga[e] = wk; wk += 2 * nslot;
-            L.dxs[e] = wk; wk += in_px;
+            L.dxs[e] = wk; wk += edge_npd(sd) * in_px;
         }
     }
     const long long node = (long long)L.B * L.C * L.Ho * L.Wo;
@@ -330,42 +262,42 @@ using namespace pcd;
 extern "C" {
 
 int pcd_version(void) { return PCD_VERSION; }
-long long pcd_launch_count(void) { return g_launches; }
+long long pcd_launch_count(void) { return g_state.launches; }
 
 int pcd_profile_enable(int on) {
 #if PCD_CUDA
-    if (on && !g_prof_ev) {
-        g_prof_ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * 2 * kMaxRecords);
+    if (on && !g_state.ev) {
+        g_state.ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * 2 * kMaxRecords);
         for (int i = 0; i < 2 * kMaxRecords; ++i)
-            if (cudaEventCreate(&g_prof_ev[i]) != cudaSuccess) return PCD_ERR_CUDA;
+            if (cudaEventCreate(&g_state.ev[i]) != cudaSuccess) return PCD_ERR_CUDA;
     }
 #endif
-    if (on) g_prof_n = 0;
-    g_prof_on = on;
+    if (on) g_state.prof_n = 0;
+    g_state.prof_on = on;
     return PCD_OK;
 }
 
-int pcd_profile_num_kernels(void) { return g_num_kernels; }
-const char* pcd_profile_kernel_name(int id) { return (id >= 0 && id < g_num_kernels) ? g_kernel_names[id] : ""; }
+int pcd_profile_num_kernels(void) { return g_state.num_kernels; }
+const char* pcd_profile_kernel_name(int id) { return (id >= 0 && id < g_state.num_kernels) ? g_state.names[id] : ""; }
 
 /* Synchronises the recorded events; adds each launch's duration to ms[kernel id] and bumps count[kernel id]. */
 int pcd_profile_collect(double* ms, long long* count, int max_kernels) {
     if (!ms || !count) return PCD_ERR_ARG;
 #if PCD_CUDA
-    for (int r = 0; r < g_prof_n; ++r) {
+    for (int r = 0; r < g_state.prof_n; ++r) {
         float t = 0.f;
-        if (cudaEventSynchronize(g_prof_ev[2 * r + 1]) != cudaSuccess) return PCD_ERR_CUDA;
-        if (cudaEventElapsedTime(&t, g_prof_ev[2 * r], g_prof_ev[2 * r + 1]) != cudaSuccess) return PCD_ERR_CUDA;
-        const int k = g_prof_kid[r];
+        if (cudaEventSynchronize(g_state.ev[2 * r + 1]) != cudaSuccess) return PCD_ERR_CUDA;
+        if (cudaEventElapsedTime(&t, g_state.ev[2 * r], g_state.ev[2 * r + 1]) != cudaSuccess) return PCD_ERR_CUDA;
+        const int k = g_state.prof_kid[r];
         if (k < max_kernels) { ms[k] += t; count[k] += 1; }
     }
 #endif
-    const int n = g_prof_n;
-    g_prof_n = 0;
+    const int n = g_state.prof_n;
+    g_state.prof_n = 0;
     return n;
 }
 int pcd_is_cuda_build(void) { return PCD_CUDA; }
-const char* pcd_last_cuda_error(void) { return g_last_err; }
+const char* pcd_last_cuda_error(void) { return g_state.last_err; }
 const char* pcd_strerror(int s) {
     switch (s) {
         case PCD_OK: return "ok";
@@ -496,7 +428,7 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
             eg[n].alpha = a->weights + e * PCD_NUM_PRIMITIVES;
             eg[n].beta = a->weights2 + e;
             eg[n].ga = a->work + L.ga[e];
-            eg[n].dxs = a->work + L.dxs[e];
+            eg[n].pd = a->work + L.dxs[e];
             q.S = L.stride[e]; q.Hs = s.H; q.Ws = s.W;
             ++n;
         }
@@ -520,7 +452,7 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
                 if (m >= kMaxSrcEdges) return PCD_ERR_ARG;
                 long long cns;
                 const float* cdn = dn_ptr(L.node_of[e], cns);
-                sg.e[m].dxs = a->work + L.dxs[e]; sg.e[m].dn = cdn; sg.e[m].dn_ns = cns;
+                sg.e[m].pd = a->work + L.dxs[e]; sg.e[m].dn = cdn; sg.e[m].dn_ns = cns;
                 sg.e[m].beta = a->weights2 + e; sg.e[m].stride = L.stride[e];
                 ++m;
             }
@@ -576,7 +508,7 @@ int pcd_mixedop_sizes_of(const pcd_mixedop_shape* s, pcd_mixedop_sizes* o) {
     o->out_floats = 4 * q.nslot();
     o->saved_floats = edge_nslots(q.S) * q.nslot();
     o->stats_doubles = edge_stats_doubles(q.c, q.S);
-    o->bwd_work_floats = 2 * q.nslot() + (long long)q.B * q.c * q.Hs * q.Ws;
+    o->bwd_work_floats = 2 * q.nslot() + (long long)edge_npd(q.S) * q.B * q.c * q.Hs * q.Ws;
     o->bwd_stats_doubles = edge_bstats_doubles(q.c);
     o->out_height = q.Ho; o->out_width = q.Wo;
     return PCD_OK;
@@ -618,13 +550,13 @@ int pcd_mixedop_backward(const pcd_mixedop_bwd_args* a, void* stream) {
     memset(&eg, 0, sizeof eg);
     eg.x = a->x; eg.x_ns = es.x_ns; eg.dn = a->grad_out; eg.dn_ns = C * q.Ho * q.Wo; eg.saved = a->saved; eg.stats = a->stats;
     eg.bstats = a->bstats; eg.par = a->params; eg.gpar = a->need_param_grads ? a->grad_params : nullptr;
-    eg.alpha = a->weights; eg.beta = nullptr; eg.ga = a->work; eg.dxs = a->work + 2 * q.nslot();
+    eg.alpha = a->weights; eg.beta = nullptr; eg.ga = a->work; eg.pd = a->work + 2 * q.nslot();
     PCD_TRY(run_edge_bwd(q, &eg, 1, a->shape.bn_eps, a->need_param_grads, stream));
     SourceGradArgs sg;
     memset(&sg, 0, sizeof sg);
     sg.B = q.B; sg.C = (int)C; sg.Hs = q.Hs; sg.Ws = q.Ws; sg.x = a->x; sg.x_ns = es.x_ns; sg.g0 = nullptr;
     sg.out = a->grad_x; sg.out_ns = es.x_ns; sg.nedges = 1;
-    sg.e[0].dxs = eg.dxs; sg.e[0].dn = a->grad_out; sg.e[0].dn_ns = eg.dn_ns; sg.e[0].beta = nullptr; sg.e[0].stride = q.S;
+    sg.e[0].pd = eg.pd; sg.e[0].dn = a->grad_out; sg.e[0].dn_ns = eg.dn_ns; sg.e[0].beta = nullptr; sg.e[0].stride = q.S;
     PCD_TRY(run_source_grad(sg, stream));
     ArchGradArgs ag;
     memset(&ag, 0, sizeof ag);

@@ -13,20 +13,6 @@
 
 namespace pcd {
 
-// dz = c0 * (dy - a - (z - m) * c1)        (BatchNorm backward, affine=False, batch statistics)
-struct DzC { float c0, a, m, c1; };
-
-PCD_HD DzC dz_consts(const double* st, int c, int bn, int j, double n, float eps, double sum_dy,
-                     double sum_dyz, float kappa) {
-    BnC b = bn_consts(st, c, bn, j, n, eps);
-    DzC r;
-    r.c0 = b.rstd * kappa;
-    r.a = (float)(sum_dy / n);
-    r.m = b.mean;
-    r.c1 = (float)((double)b.rstd * (double)b.rstd * (sum_dyz - (double)b.mean * sum_dy) / n);
-    return r;
-}
-
 // ---- node_stats -------------------------------------------------------------------------------------
 struct EdgeS {
     const float* x;
@@ -110,533 +96,9 @@ PCD_HD void node_stats_body(const NodeStatsArgs& a, int bx, int n, int ez, float
     });
 }
 
-// ---- shared pieces of the edge backward kernels -----------------------------------------------------
-struct EdgeG {
-    const float* x;        // source state
-    long long x_ns;
-    const float* dn;       // grad of the node this edge feeds (B, C, Ho, Wo) view
-    long long dn_ns;
-    const float* saved;
-    const double* stats;
-    double* bstats;
-    const float* par;
-    float* gpar;           // may be null when need_wgrad == 0
-    const float* alpha;
-    const float* beta;     // null => 1
-    float* ga;             // 2 slots: grad wrt BN(A3) / BN(A5) outputs (post ReLU mask)
-    float* dxs;            // (B, c, Hs, Ws): grad wrt x[:, :c] from the 7 candidate ops
-};
-
-struct EdgeBwdArgs {
-    int B, Hs, Ws, Ho, Wo, S;
-    int TH, TW, tiles_x;
-    float eps;
-    int nedges, need_wgrad;
-    EdgeG e[kMaxEdgesPerLaunch];
-};
-
-// dWpw[co][ci] += sum_p DZ[co][p] * t[ci][p] over the tile (t read from the saved slot).
-// Tasks: (C/4)^2 output groups x NSL pixel slices; 16 partials per task.
-template <int C>
-PCD_HD void wgrad_pw(const float* DZ, const float* t_slot, float* gw, float* P, float* P2, const Geo& g) {
-    constexpr int NOG = (C / 4) * (C / 4), NSL = 256 / NOG;
-    const int NPIX = g.TH * g.TW, PPS = (NPIX + NSL - 1) / NSL;
-    PCD_FOR(task, 256) {
-        const int og = task / NSL, sl = task - og * NSL;
-        const int co0 = (og / (C / 4)) * 4, ci0 = (og % (C / 4)) * 4;
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
-        for (int pp = sl * PPS; pp < (sl + 1) * PPS && pp < NPIX; ++pp) {
-            const int oyl = pp / g.TW, oxl = pp - oyl * g.TW;
-            const int oy = g.oy0 + oyl, ox = g.ox0 + oxl;
-            if (oy >= g.Ho || ox >= g.Wo) continue;
-            float tv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tv[k] = t_slot[out_index(g, C, ci0 + k, oy, ox)];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float d = DZ[(co0 + i) * NPIX + pp];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(d, tv[k], acc[i][k]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) P[(i * 4 + k) * 256 + task] = acc[i][k];
-    }
-    reduce_columns<8>(P, P2, 16, NOG, NSL, 256, [&](int og, int k, float v) {
-        const int co = (og / (C / 4)) * 4 + (k >> 2), ci = (og % (C / 4)) * 4 + (k & 3);
-        pcd_atomic_add(gw + co * C + ci, v);
-    });
-}
-
-// dz on the haloed output tile -> dt = Wpw^T dz into DT[C][RH][IW]; centre dz into DZ[C][NPIX].
-// dy comes from `dy_base` (+ channel stride dy_cs, channel index = dy_ch0 + j*dy_chm), z from z_slot.
-template <int C>
-PCD_HD void dz_dt_tile(float* DT, float* DZ, int RH, int IW, int halo_y, const float* dy_img /* image n */,
-                       long long dy_cs, int dy_chm, const float* z_slot, const float* w_pw, const float* COEF,
-                       const Geo& g) {
-    const int NPIX = g.TH * g.TW;
-    PCD_FOR(i, RH * IW) {
-        const int r = i / IW, col = i - r * IW;
-        const int oyl = r - halo_y, oxl = col - 4;
-        const int oy = g.oy0 + oyl, ox = g.ox0 + oxl;
-        float dz[C], dt[C];
-        const bool in = (oy >= 0 && oy < g.Ho && ox >= 0 && ox < g.Wo);
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            float v = 0.f;
-            if (in) {
-                const float dy = dy_img[(long long)(j * dy_chm) * dy_cs + (long long)oy * g.Wo + ox];
-                const float z = z_slot[out_index(g, C, j, oy, ox)];
-                v = COEF[4 * j] * (dy - COEF[4 * j + 1] - (z - COEF[4 * j + 2]) * COEF[4 * j + 3]);
-            }
-            dz[j] = v;
-        }
-#pragma unroll
-        for (int ci = 0; ci < C; ++ci) {
-            float s = 0.f;
-#pragma unroll
-            for (int co = 0; co < C; ++co) s = fmaf(w_pw[co * C + ci], dz[co], s);
-            dt[ci] = s;
-        }
-#pragma unroll
-        for (int ci = 0; ci < C; ++ci) DT[(ci * RH + r) * IW + col] = dt[ci];
-        if (oyl >= 0 && oyl < g.TH && oxl >= 0 && oxl < g.TW) {
-#pragma unroll
-            for (int j = 0; j < C; ++j) DZ[j * NPIX + oyl * g.TW + oxl] = dz[j];
-        }
-    }
-}
-
-// dWdw[ch][tap] += sum over tile patches of dt(centre of DT) * in(tile)
-template <int C, int KS, int DIL, int S, bool RELU>
-PCD_HD void wgrad_dw(const float* DT, int RH, int IW, int halo_y, const float* IN, int in_rows, int in_pitch,
-                     int in_halo_y, float* gw, float* P, float* P2, const Geo& g) {
-    constexpr int PAD = DIL * (KS - 1) / 2;
-    const int PW4 = g.TW / 4, NPATCH = (g.TH / 4) * PW4, NT = C * NPATCH;
-    PCD_FOR(task, NT) {
-        const int ch = task / NPATCH, patch = task - ch * NPATCH;
-        const int py = (patch / PW4) * 4, px = (patch % PW4) * 4;
-        float dt[4][4], acc[KS * KS];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const F4 v = *reinterpret_cast<const F4*>(DT + (ch * RH + py + i + halo_y) * IW + px + 4);
-            dt[i][0] = v.x; dt[i][1] = v.y; dt[i][2] = v.z; dt[i][3] = v.w;
-        }
-#pragma unroll
-        for (int k = 0; k < KS * KS; ++k) acc[k] = 0.f;
-        dw_wgrad_patch<KS, DIL, S, RELU>(IN + ch * in_rows * in_pitch, in_pitch, S * py - PAD + in_halo_y, S * px,
-                                         dt, acc);
-#pragma unroll
-        for (int k = 0; k < KS * KS; ++k) P[k * NT + task] = acc[k];
-    }
-    reduce_columns<8>(P, P2, KS * KS, C, NPATCH, NT, [&](int ch, int k, float v) {
-        pcd_atomic_add(gw + ch * KS * KS + k, v);
-    });
-}
-
-// ---- edge_bwdB ------------------------------------------------------------------------------------------
-PCD_HOSTDEV size_t bwdB_smem_floats(int C, int TH, int TW) {
-    const size_t tile = (size_t)C * (TH + 8) * (TW + 8);
-    const int NPATCH = (TH / 4) * (TW / 4);
-    size_t p = (size_t)25 * C * NPATCH;
-    if (p < 16 * 256) p = 16 * 256;
-    return 2 * tile + (size_t)C * TH * TW + p + 4096 + 6 * C + 64;
-}
-
-template <int C, int KS>
-PCD_HD void bwdB_half(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, int half, float* smem) {
-    constexpr int PAD = (KS - 1) / 2;
-    const int S = a.S, TH = g.TH, TW = g.TW, NPIX = TH * TW, RH = TH + 8, IW = TW + 8;
-    const int PW4 = TW / 4, NPATCH = (TH / 4) * PW4;
-    float* DT = smem;
-    float* Q = DT + C * RH * IW;
-    float* DZ = Q + C * RH * IW;
-    float* P = DZ + C * NPIX;
-    size_t psz = (size_t)25 * C * NPATCH;
-    if (psz < 16 * 256) psz = 16 * 256;
-    float* P2 = P + psz;
-    float* COEF = P2 + 4096;
-    float* BNA = COEF + 4 * C;
-    const int uA = half ? 2 : 0, uB = uA + 1;
-    const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
-    const double cnt = (double)a.B * a.Ho * a.Wo;
-    const float beta = e.beta ? e.beta[0] : 1.f;
-    const float kappa = beta * e.alpha[half ? 5 : 4];
-    PCD_FOR(j, C) {
-        const int bnB = bn_unit(S, uB);
-        DzC d = dz_consts(e.stats, C, bnB, j, cnt, a.eps, e.bstats[bs_s0() * C + j], e.bstats[bs_sz(bnB) * C + j], kappa);
-        COEF[4 * j] = d.c0; COEF[4 * j + 1] = d.a; COEF[4 * j + 2] = d.m; COEF[4 * j + 3] = d.c1;
-        BnC b = bn_consts(e.stats, C, bn_unit(S, uA), j, cnt, a.eps);
-        BNA[2 * j] = b.mean; BNA[2 * j + 1] = b.rstd;
-    }
-    PCD_SYNC();
-    const float* zA = e.saved + slot_z(uA) * nslot;
-    const float* zB = e.saved + slot_z(uB) * nslot;
-    const float* w_dw = e.par + edge_dw_off(C, S, uB);
-    const float* w_pw = e.par + edge_pw_off(C, S, uB);
-    dz_dt_tile<C>(DT, DZ, RH, IW, 4, e.dn + (long long)g.n * e.dn_ns, (long long)a.Ho * a.Wo, 4, zB, w_pw, COEF, g);
-    PCD_FOR(i, C * RH * IW) {
-        const int ch = i / (RH * IW), r = (i / IW) % RH, col = i % IW;
-        const int oy = g.oy0 - 4 + r, ox = g.ox0 - 4 + col;
-        float v = 0.f;
-        if (oy >= 0 && oy < a.Ho && ox >= 0 && ox < a.Wo)
-            v = relu((zA[out_index(g, C, ch, oy, ox)] - BNA[2 * ch]) * BNA[2 * ch + 1]);
-        Q[i] = v;
-    }
-    PCD_SYNC();
-    if (a.need_wgrad)
-        wgrad_pw<C>(DZ, e.saved + slot_t(uB) * nslot, e.gpar + edge_pw_off(C, S, uB), P, P2, g);
-    // grad wrt relu(bn(zA)) = flipped depthwise correlation of dt; mask by the ReLU; sums for BN-A backward
-    float* ga = e.ga + half * nslot;
-    PCD_FOR(task, C * NPATCH) {
-        const int ch = task / NPATCH, patch = task - ch * NPATCH;
-        const int py = (patch / PW4) * 4, px = (patch % PW4) * 4;
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        dw_patch<KS, 1, 1, true, false>(DT + ch * RH * IW, IW, py - PAD + 4, px, w_dw + ch * KS * KS, acc);
-        float s = 0.f, sz = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int oy = g.oy0 + py + i;
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ox = g.ox0 + px + j;
-                const float q = Q[(ch * RH + py + i + 4) * IW + px + j + 4];
-                o[j] = q > 0.f ? acc[i][j] : 0.f;
-                if (oy < a.Ho && ox < a.Wo) {
-                    s += o[j];
-                    sz = fmaf(o[j], zA[out_index(g, C, ch, oy, ox)], sz);
-                }
-            }
-            store4(ga, g, C, ch, oy, g.ox0 + px, o);
-        }
-        P[task] = s;
-        P[C * NPATCH + task] = sz;
-    }
-    reduce_columns<8>(P, P2, 2, C, NPATCH, C * NPATCH, [&](int ch, int k, float v) {
-        pcd_atomic_add(e.bstats + (bs_ga(half) + k) * C + ch, (double)v);
-    });
-    if (a.need_wgrad) {
-        wgrad_dw<C, KS, 1, 1, false>(DT, RH, IW, 4, Q, RH, IW, 4, e.gpar + edge_dw_off(C, S, uB), P, P2, g);
-    }
-}
-
-template <int C>
-PCD_HD void bwdB_body(const EdgeBwdArgs& a, int bx, int n, int ez, float* smem) {
-    const EdgeG& e = a.e[ez];
-    Geo g;
-    g.n = n; g.TH = a.TH; g.TW = a.TW; g.Ho = a.Ho; g.Wo = a.Wo;
-    g.oy0 = (bx / a.tiles_x) * a.TH;
-    g.ox0 = (bx % a.tiles_x) * a.TW;
-    bwdB_half<C, 3>(a, e, g, 0, smem);
-    PCD_SYNC();
-    bwdB_half<C, 5>(a, e, g, 1, smem);
-}
-
-// ---- edge_bwdA ------------------------------------------------------------------------------------------
-PCD_HOSTDEV size_t bwdA_smem_floats(int C, int S, int TH, int TW) {
-    const size_t xin = (size_t)C * (S * TH + 8) * (S * TW + 8);
-    const size_t tile = (size_t)C * (TH + 8) * (TW + 8);
-    const int NPATCH = (TH / 4) * (TW / 4);
-    size_t p = (size_t)25 * C * NPATCH;
-    if (p < 16 * 256) p = 16 * 256;
-    if (p < tile) p = tile;     // P aliases the second pooling tile
-    return xin + tile + p + (size_t)C * TH * TW + (size_t)C * S * TH * S * TW + 4096 + 4 * C + 64;
-}
-
-// gather d relu(x) for one stride-2 depthwise conv: in pixel q gets sum_tap w[tap] * dt[(q + PAD - tap*DIL)/2]
-template <int KS, int DIL>
-PCD_HD void dw_bwd_data_s2(const float* dtp /* plane [RH][IW], halo_y 4, col halo 4 */, int IW, int qy0, int qx0,
-                           const float* w, float (&acc)[4][4]) {
-    constexpr int PAD = DIL * (KS - 1) / 2;
-#pragma unroll
-    for (int iy = 0; iy < 4; ++iy)
-#pragma unroll
-        for (int ky = 0; ky < KS; ++ky) {
-            const int ty = iy + PAD - ky * DIL;               // qy0 is a multiple of 4 (even)
-            if ((ty & 1) != 0) continue;
-            const int prow = (qy0 + ty) / 2 + 4;
-#pragma unroll
-            for (int ix = 0; ix < 4; ++ix)
-#pragma unroll
-                for (int kx = 0; kx < KS; ++kx) {
-                    const int tx = ix + PAD - kx * DIL;
-                    if ((tx & 1) != 0) continue;
-                    const int pcol = (qx0 + tx) / 2 + 4;
-                    acc[iy][ix] = fmaf(w[ky * KS + kx], dtp[prow * IW + pcol], acc[iy][ix]);
-                }
-        }
-}
-
-template <int C, int S, int KS, int DIL>
-PCD_HD void bwdA_unit(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, int u, const float* dy_img, long long dy_cs,
-                      int dy_chm, const float* XIN, float* DT, float* DZ, float* ACC, float* P, float* P2,
-                      const float* COEF) {
-    constexpr int PAD = DIL * (KS - 1) / 2;
-    const int TH = g.TH, TW = g.TW, RH = TH + 8, IW = TW + 8, IH = S * TH + 8, XW = S * TW + 8;
-    const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
-    const float* w_dw = e.par + edge_dw_off(C, S, u);
-    const float* w_pw = e.par + edge_pw_off(C, S, u);
-    dz_dt_tile<C>(DT, DZ, RH, IW, 4, dy_img, dy_cs, dy_chm, e.saved + slot_z(u) * nslot, w_pw, COEF, g);
-    PCD_SYNC();
-    if (a.need_wgrad) wgrad_pw<C>(DZ, e.saved + slot_t(u) * nslot, e.gpar + edge_pw_off(C, S, u), P, P2, g);
-    // d relu(xs) accumulated into ACC[C][S*TH][S*TW]
-    const int AH = S * TH, AW = S * TW;
-    const int APW4 = AW / 4, ANP = (AH / 4) * APW4;
-    PCD_FOR(task, C * ANP) {
-        const int ch = task / ANP, patch = task - ch * ANP;
-        const int qy = (patch / APW4) * 4, qx = (patch % APW4) * 4;
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        if (S == 1)
-            dw_patch<KS, DIL, 1, true, false>(DT + ch * RH * IW, IW, qy - PAD + 4, qx, w_dw + ch * KS * KS, acc);
-        else
-            dw_bwd_data_s2<KS, DIL>(DT + ch * RH * IW, IW, qy, qx, w_dw + ch * KS * KS, acc);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ACC[(ch * AH + qy + i) * AW + qx + j] += acc[i][j];
-    }
-    PCD_SYNC();
-    if (a.need_wgrad)
-        wgrad_dw<C, KS, DIL, S, true>(DT, RH, IW, 4, XIN, IH, XW, 4, e.gpar + edge_dw_off(C, S, u), P, P2, g);
-}
-
-template <int C, int S>
-PCD_HD void bwdA_body(const EdgeBwdArgs& a, int bx, int n, int ez, float* smem) {
-    const EdgeG& e = a.e[ez];
-    Geo g;
-    g.n = n; g.TH = a.TH; g.TW = a.TW; g.Ho = a.Ho; g.Wo = a.Wo;
-    g.oy0 = (bx / a.tiles_x) * a.TH;
-    g.ox0 = (bx % a.tiles_x) * a.TW;
-    const int TH = a.TH, TW = a.TW, NPIX = TH * TW, RH = TH + 8, IW = TW + 8;
-    const int IH = S * TH + 8, XW = S * TW + 8, AH = S * TH, AW = S * TW;
-    const int NPATCH = (TH / 4) * (TW / 4);
-    const size_t tile = (size_t)C * RH * IW;
-    size_t psz = (size_t)25 * C * NPATCH;
-    if (psz < 16 * 256) psz = 16 * 256;
-    if (psz < tile) psz = tile;
-    float* XIN = smem;
-    float* DT = XIN + C * IH * XW;
-    float* P = DT + tile;          // also the second pooling tile
-    float* DT2 = P;
-    float* DZ = P + psz;
-    float* ACC = DZ + C * NPIX;
-    float* P2 = ACC + C * AH * AW;
-    float* COEF = P2 + 4096;
-    const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
-    const long long HWo = (long long)a.Ho * a.Wo;
-    const double cnt = (double)a.B * a.Ho * a.Wo;
-    const float beta = e.beta ? e.beta[0] : 1.f;
-    const int iy0 = S * g.oy0 - 4, ix0 = S * g.ox0 - 4;
-    const float* xg = e.x + (long long)n * e.x_ns;
-    const float* dn_img = e.dn + (long long)n * e.dn_ns;
-
-    PCD_FOR(i, C * IH * XW) {
-        const int ch = i / (IH * XW), r = (i / XW) % IH, col = i % XW;
-        const int gy = iy0 + r, gx = ix0 + col;
-        float v = 0.f;
-        if (gy >= 0 && gy < a.Hs && gx >= 0 && gx < a.Ws) v = xg[((long long)ch * a.Hs + gy) * a.Ws + gx];
-        XIN[i] = v;
-    }
-    PCD_FOR(i, C * AH * AW) ACC[i] = 0.f;
-    PCD_SYNC();
-
-    // ---- the four conv units that read relu(xs) ------------------------------------------------------
-    for (int k = 0; k < 4; ++k) {
-        const int u = (k == 0) ? 0 : (k == 1) ? 2 : (k == 2) ? 4 : 5;
-        PCD_FOR(j, C) {
-            DzC d;
-            const int bn = bn_unit(S, u);
-            if (k < 2)   // A units: dy = GA (already includes every upstream factor)
-                d = dz_consts(e.stats, C, bn, j, cnt, a.eps, e.bstats[bs_ga(k) * C + j], e.bstats[(bs_ga(k) + 1) * C + j], 1.f);
-            else
-                d = dz_consts(e.stats, C, bn, j, cnt, a.eps, e.bstats[bs_s0() * C + j], e.bstats[bs_sz(bn) * C + j],
-                              beta * e.alpha[k == 2 ? 6 : 7]);
-            COEF[4 * j] = d.c0; COEF[4 * j + 1] = d.a; COEF[4 * j + 2] = d.m; COEF[4 * j + 3] = d.c1;
-        }
-        PCD_SYNC();
-        const float* ga_img = e.ga + (k < 2 ? k : 0) * nslot + (long long)n * C * HWo;
-        if (k == 0) bwdA_unit<C, S, 3, 1>(a, e, g, u, ga_img, HWo, 1, XIN, DT, DZ, ACC, P, P2, COEF);
-        else if (k == 1) bwdA_unit<C, S, 5, 1>(a, e, g, u, ga_img, HWo, 1, XIN, DT, DZ, ACC, P, P2, COEF);
-        else if (k == 2) bwdA_unit<C, S, 3, 2>(a, e, g, u, dn_img, HWo, 4, XIN, DT, DZ, ACC, P, P2, COEF);
-        else bwdA_unit<C, S, 5, 2>(a, e, g, u, dn_img, HWo, 4, XIN, DT, DZ, ACC, P, P2, COEF);
-        PCD_SYNC();
-    }
-
-    // ---- skip_connect at stride 2: FactorizedReduce backward ----------------------------------------
-    if (S == 2) {
-        PCD_FOR(j, C) {
-            DzC d = dz_consts(e.stats, C, bn_f(), j, cnt, a.eps, e.bstats[bs_s0() * C + j],
-                              e.bstats[bs_sz(bn_f()) * C + j], beta * e.alpha[3]);
-            COEF[4 * j] = d.c0; COEF[4 * j + 1] = d.a; COEF[4 * j + 2] = d.m; COEF[4 * j + 3] = d.c1;
-        }
-        PCD_SYNC();
-        const float* F = e.saved + slot_f() * nslot;
-        PCD_FOR(pp, NPIX) {
-            const int oyl = pp / TW, oxl = pp - oyl * TW;
-            const int oy = g.oy0 + oyl, ox = g.ox0 + oxl;
-            const bool in = oy < a.Ho && ox < a.Wo;
-            float dz[C];
-#pragma unroll
-            for (int j = 0; j < C; ++j) {
-                float v = 0.f;
-                if (in) {
-                    const float h = dn_img[(long long)(4 * j) * HWo + (long long)oy * a.Wo + ox];
-                    v = COEF[4 * j] * (h - COEF[4 * j + 1] - (F[out_index(g, C, j, oy, ox)] - COEF[4 * j + 2]) * COEF[4 * j + 3]);
-                }
-                dz[j] = v;
-                DZ[j * NPIX + pp] = v;
-            }
-#pragma unroll
-            for (int ci = 0; ci < C; ++ci) {
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int co = 0; co < C / 2; ++co) {
-                    s0 = fmaf(e.par[co * C + ci], dz[co], s0);
-                    s1 = fmaf(e.par[(co + C / 2) * C + ci], dz[co + C / 2], s1);
-                }
-                ACC[(ci * AH + 2 * oyl) * AW + 2 * oxl] += s0;
-                ACC[(ci * AH + 2 * oyl + 1) * AW + 2 * oxl + 1] += s1;
-            }
-        }
-        PCD_SYNC();
-        if (a.need_wgrad) {
-            // dW_fr[co][ci] += sum_p dz[co][p] * relu(x[ci][2p + off(co)])
-            constexpr int NOG = (C / 4) * (C / 4), NSL = 256 / NOG;
-            const int PPS = (NPIX + NSL - 1) / NSL;
-            PCD_FOR(task, 256) {
-                const int og = task / NSL, sl = task - og * NSL;
-                const int co0 = (og / (C / 4)) * 4, ci0 = (og % (C / 4)) * 4;
-                float acc[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
-                for (int pp = sl * PPS; pp < (sl + 1) * PPS && pp < NPIX; ++pp) {
-                    const int oyl = pp / TW, oxl = pp - oyl * TW;
-                    float rv[2][4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        rv[0][k] = relu(XIN[((ci0 + k) * IH + 2 * oyl + 4) * XW + 2 * oxl + 4]);
-                        rv[1][k] = relu(XIN[((ci0 + k) * IH + 2 * oyl + 5) * XW + 2 * oxl + 5]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float d = DZ[(co0 + i) * NPIX + pp];
-                        const int off = (co0 + i) >= C / 2 ? 1 : 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(d, rv[off][k], acc[i][k]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) P[(i * 4 + k) * 256 + task] = acc[i][k];
-            }
-            reduce_columns<8>(P, P2, 16, NOG, NSL, 256, [&](int og, int k, float v) {
-                const int co = (og / (C / 4)) * 4 + (k >> 2), ci = (og % (C / 4)) * 4 + (k & 3);
-                pcd_atomic_add(e.gpar + co * C + ci, v);
-            });
-        }
-    }
-
-    // ---- ReLU mask on the conv paths; identity skip at stride 1 -----------------------------------------
-    PCD_FOR(i, C * AH * AW) {
-        const int ch = i / (AH * AW), qy = (i / AW) % AH, qx = i % AW;
-        const float xv = XIN[(ch * IH + qy + 4) * XW + qx + 4];
-        float v = xv > 0.f ? ACC[i] : 0.f;
-        if (S == 1) {
-            const int oy = g.oy0 + qy, ox = g.ox0 + qx;
-            if (oy < a.Ho && ox < a.Wo)
-                v = fmaf(beta * e.alpha[3], dn_img[(long long)(4 * ch) * HWo + (long long)oy * a.Wo + ox], v);
-        }
-        ACC[i] = v;
-    }
-    PCD_SYNC();
-
-    // ---- pools: dz on the 1-haloed output tile, then gather over the windows containing each input px --
-    for (int pool = 0; pool < 2; ++pool) {
-        const int bn = pool ? bn_p2() : bn_p1();
-        PCD_FOR(j, C) {
-            DzC d = dz_consts(e.stats, C, bn, j, cnt, a.eps, e.bstats[bs_s0() * C + j], e.bstats[bs_sz(bn) * C + j],
-                              beta * e.alpha[pool ? 2 : 1]);
-            COEF[4 * j] = d.c0; COEF[4 * j + 1] = d.a; COEF[4 * j + 2] = d.m; COEF[4 * j + 3] = d.c1;
-        }
-        PCD_SYNC();
-        const float* Z = e.saved + (pool ? slot_p2() : slot_p1()) * nslot;
-        PCD_FOR(i, C * RH * IW) {
-            const int ch = i / (RH * IW), r = (i / IW) % RH, col = i % IW;
-            const int oyl = r - 4, oxl = col - 4;
-            const int oy = g.oy0 + oyl, ox = g.ox0 + oxl;
-            float dzv = 0.f, code = -1.f;
-            if (oyl >= -1 && oyl <= TH && oxl >= -1 && oxl <= TW && oy >= 0 && oy < a.Ho && ox >= 0 && ox < a.Wo) {
-                const float h = dn_img[(long long)(4 * ch) * HWo + (long long)oy * a.Wo + ox];
-                dzv = COEF[4 * ch] * (h - COEF[4 * ch + 1] - (Z[out_index(g, C, ch, oy, ox)] - COEF[4 * ch + 2]) * COEF[4 * ch + 3]);
-                float m = -INFINITY;
-                int cntv = 0, best = -1;
-                for (int dy = 0; dy < 3; ++dy)
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int gy = S * oy + dy - 1, gx = S * ox + dx - 1;
-                        if (gy >= 0 && gy < a.Hs && gx >= 0 && gx < a.Ws) {
-                            const float v = XIN[(ch * IH + S * oyl + dy + 3) * XW + S * oxl + dx + 3];
-                            if (v > m || best < 0) { m = v; best = dy * 3 + dx; }
-                            ++cntv;
-                        }
-                    }
-                if (pool) dzv = dzv / (float)cntv;
-                code = (float)best;
-            }
-            DT[i] = dzv;
-            if (!pool) DT2[i] = code;
-        }
-        PCD_SYNC();
-        PCD_FOR(i, C * AH * AW) {
-            const int ch = i / (AH * AW), qy = (i / AW) % AH, qx = i % AW;
-            float s = 0.f;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const int ty = qy + 1 - dy;
-                if (ty % S != 0) continue;
-                const int pr = ty / S + 4;          // ty >= -1; -1 only when S == 1
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int tx = qx + 1 - dx;
-                    if (tx % S != 0) continue;
-                    const int pc = tx / S + 4;
-                    const int idx = (ch * RH + pr) * IW + pc;
-                    if (pool) s += DT[idx];
-                    else if (DT2[idx] == (float)(dy * 3 + dx)) s += DT[idx];
-                }
-            }
-            ACC[i] += s;
-        }
-        PCD_SYNC();
-    }
-
-    PCD_FOR(i, C * AH * AW) {
-        const int ch = i / (AH * AW), qy = (i / AW) % AH, qx = i % AW;
-        const int gy = S * g.oy0 + qy, gx = S * g.ox0 + qx;
-        if (gy < a.Hs && gx < a.Ws) e.dxs[(((long long)n * C + ch) * a.Hs + gy) * a.Ws + gx] = ACC[i];
-    }
-}
-
 // ---- source_grad ----------------------------------------------------------------------------------------
 struct SrcEdge {
-    const float* dxs;      // (B, c, Hs, Ws)
+    const float* pd;       // partial d xs slots of this edge (see EdgeG::pd), each (B, c, Hs, Ws)
     const float* dn;       // node grad of the consumer (B, C, Ho, Wo) view
     long long dn_ns;
     const float* beta;     // null => 1
@@ -647,7 +109,7 @@ constexpr int kMaxSrcEdges = 4;
 
 struct SourceGradArgs {
     int B, C, Hs, Ws;
-    const float* x;        // the source state itself (needed for the 2x2 max-pool argmax at stride 2)
+    const float* x;        // the source state itself (ReLU mask; 2x2 max-pool argmax at stride 2)
     long long x_ns;
     const float* g0;       // optional initial grad (cell-output slice), same view geometry as `out`
     long long g0_ns;
@@ -657,18 +119,56 @@ struct SourceGradArgs {
     SrcEdge e[kMaxSrcEdges];
 };
 
+// d x[:, ch<c]  = g0 + sum_e [ relu'(x) * (A3 + A5 + D3 + D5 (+ FR)) + max-pool + avg-pool(+identity) partials ]
+// d x[:, q*c+j] = g0 + sum_e beta_e * (dN_e[:, 4j+q]  |  routed through the 2x2 max-pool argmax at stride 2)
 PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int n) {
     const int HW = a.Hs * a.Ws, c = a.C / 4;
     const int p0 = bx * 4096;
     const int npx = (HW - p0) < 4096 ? (HW - p0) : 4096;
     float* ob = a.out + (long long)n * a.out_ns + (long long)ch * HW;
+    const float* xb = a.x + (long long)n * a.x_ns + (long long)ch * HW;
+    const long long pslot = (long long)a.B * c * HW;
+    const bool vec = (HW % 4 == 0) && (p0 % 4 == 0) && ((((uintptr_t)ob) | ((uintptr_t)xb)) & 15) == 0 &&
+                     (!a.g0 || ((((uintptr_t)(a.g0 + (long long)n * a.g0_ns + (long long)ch * HW)) & 15) == 0));
+    if (ch < c && vec) {
+        PCD_FOR(i4, npx / 4) {
+            const int p = p0 + i4 * 4;
+            F4 v = {0.f, 0.f, 0.f, 0.f};
+            if (a.g0) v = *reinterpret_cast<const F4*>(a.g0 + (long long)n * a.g0_ns + (long long)ch * HW + p);
+            const F4 xv = *reinterpret_cast<const F4*>(xb + p);
+            for (int k = 0; k < a.nedges; ++k) {
+                const SrcEdge& e = a.e[k];
+                const float* pd = e.pd + ((long long)n * c + ch) * HW + p;
+                F4 m = {0.f, 0.f, 0.f, 0.f};
+                for (int s = 0; s < 4; ++s) {
+                    const F4 t = *reinterpret_cast<const F4*>(pd + s * pslot);
+                    m.x += t.x; m.y += t.y; m.z += t.z; m.w += t.w;
+                }
+                if (e.stride == 2) {
+                    const F4 t = *reinterpret_cast<const F4*>(pd + 6 * pslot);
+                    m.x += t.x; m.y += t.y; m.z += t.z; m.w += t.w;
+                }
+                const F4 p4 = *reinterpret_cast<const F4*>(pd + 4 * pslot);
+                const F4 p5 = *reinterpret_cast<const F4*>(pd + 5 * pslot);
+                v.x += (xv.x > 0.f ? m.x : 0.f) + p4.x + p5.x;
+                v.y += (xv.y > 0.f ? m.y : 0.f) + p4.y + p5.y;
+                v.z += (xv.z > 0.f ? m.z : 0.f) + p4.z + p5.z;
+                v.w += (xv.w > 0.f ? m.w : 0.f) + p4.w + p5.w;
+            }
+            *reinterpret_cast<F4*>(ob + p) = v;
+        }
+        return;
+    }
     PCD_FOR(i, npx) {
         const int p = p0 + i;
         float v = a.g0 ? a.g0[(long long)n * a.g0_ns + (long long)ch * HW + p] : 0.f;
         for (int k = 0; k < a.nedges; ++k) {
             const SrcEdge& e = a.e[k];
             if (ch < c) {
-                v += e.dxs[((long long)n * c + ch) * HW + p];
+                const float* pd = e.pd + ((long long)n * c + ch) * HW + p;
+                float m = pd[0] + pd[pslot] + pd[2 * pslot] + pd[3 * pslot];
+                if (e.stride == 2) m += pd[6 * pslot];
+                v += (xb[p] > 0.f ? m : 0.f) + pd[4 * pslot] + pd[5 * pslot];
             } else {
                 const int q = ch / c, j = ch - q * c;     // x channel q*c + j  <->  node channel 4j + q
                 const float beta = e.beta ? e.beta[0] : 1.f;

@@ -8,281 +8,9 @@
 //   combine : per NODE: sum over incoming edges of beta * [ sum_k w_k BN(op_k) | bypass ] written
 //             channel-shuffled straight into the node's slice of the cell output (model_search.py:90)
 #pragma once
-#include "pcd_common.cuh"
+#include "pcd_edge.cuh"
 
 namespace pcd {
-
-struct EdgeF {
-    const float* x;        // source state (B, C, Hs, Ws)
-    long long x_ns;        // its batch stride (floats)
-    const float* par;      // edge parameter block
-    float* saved;          // edge saved-activation slots
-    double* stats;         // edge forward sums
-};
-
-struct PassArgs {
-    int B, Hs, Ws, Ho, Wo, S;
-    int TH, TW, tiles_x;
-    float eps;
-    int nedges;
-    EdgeF e[kMaxEdgesPerLaunch];
-};
-
-struct Geo {
-    int n, oy0, ox0, TH, TW, Ho, Wo;
-};
-
-PCD_HD long long out_index(const Geo& g, int C, int ch, int oy, int ox) {
-    return (((long long)g.n * C + ch) * g.Ho + oy) * g.Wo + ox;
-}
-
-// store 4 consecutive pixels of row oy starting at ox (masked at the image edge)
-PCD_HD void store4(float* base, const Geo& g, int C, int ch, int oy, int ox, const float (&v)[4]) {
-    if (oy >= g.Ho) return;
-    float* p = base + out_index(g, C, ch, oy, ox);
-    if (ox + 3 < g.Wo && (((uintptr_t)p) & 15) == 0) {
-        F4 t = {v[0], v[1], v[2], v[3]};
-        *reinterpret_cast<F4*>(p) = t;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (ox + j < g.Wo) p[j] = v[j];
-    }
-}
-
-// One depthwise->pointwise unit on a shared-memory input tile.
-//   plane tile: [C][rows][pitch], column origin at image col S*ox0-4, row origin at image row S*oy0-halo_y
-template <int C, int KS, int DIL, int S, bool RELU>
-PCD_HD void unit_forward(const float* tile, int rows, int pitch, int halo_y, const float* w_dw,
-                         const float* w_pw, float* T, float* P, float* P2, float* t_out, float* z_out,
-                         double* st /* sum[C], sumsq[C] of this BN */, const Geo& g) {
-    constexpr int PAD = DIL * (KS - 1) / 2;
-    const int TH = g.TH, TW = g.TW, NPIX = TH * TW, NSTRIP = NPIX / 4, PW4 = TW / 4;
-    const int NPATCH = (TH / 4) * PW4;
-    PCD_FOR(task, C * NPATCH) {
-        const int ch = task / NPATCH, patch = task - ch * NPATCH;
-        const int py = (patch / PW4) * 4, px = (patch % PW4) * 4;
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        dw_patch<KS, DIL, S, false, RELU>(tile + ch * rows * pitch, pitch, S * py - PAD + halo_y, S * px,
-                                          w_dw + ch * KS * KS, acc);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            F4 v = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
-            *reinterpret_cast<F4*>(T + ch * NPIX + (py + i) * TW + px) = v;
-            store4(t_out, g, C, ch, g.oy0 + py + i, g.ox0 + px, acc[i]);
-        }
-    }
-    PCD_SYNC();
-    constexpr int NCG = C / 4;
-    PCD_FOR(task, NCG * NSTRIP) {
-        const int cg = task / NSTRIP, strip = task - cg * NSTRIP;
-        const int oyl = strip / PW4, oxl = (strip - oyl * PW4) * 4;
-        float z[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) z[i][j] = 0.f;
-#pragma unroll
-        for (int ci = 0; ci < C; ++ci) {
-            const F4 t = *reinterpret_cast<const F4*>(T + ci * NPIX + strip * 4);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float w = w_pw[(cg * 4 + i) * C + ci];
-                z[i][0] = fmaf(w, t.x, z[i][0]);
-                z[i][1] = fmaf(w, t.y, z[i][1]);
-                z[i][2] = fmaf(w, t.z, z[i][2]);
-                z[i][3] = fmaf(w, t.w, z[i][3]);
-            }
-        }
-        const int oy = g.oy0 + oyl, ox = g.ox0 + oxl;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            store4(z_out, g, C, cg * 4 + i, oy, ox, z[i]);
-            float s = 0.f, q = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (oy < g.Ho && ox + j < g.Wo) {
-                    s += z[i][j];
-                    q = fmaf(z[i][j], z[i][j], q);
-                }
-            P[(2 * i) * (NCG * NSTRIP) + task] = s;
-            P[(2 * i + 1) * (NCG * NSTRIP) + task] = q;
-        }
-    }
-    reduce_columns(P, P2, 8, NCG, NSTRIP, NCG * NSTRIP, [&](int grp, int k, float v) {
-        pcd_atomic_add(st + (k & 1) * C + grp * 4 + (k >> 1), (double)v);
-    });
-}
-
-PCD_HOSTDEV size_t passA_smem_floats(int C, int S, int TH, int TW) {
-    const int IH = S * TH + 8, IW = S * TW + 8;
-    return (size_t)C * IH * IW + (size_t)C * TH * TW * 2 + 4 * C * 32 + 64;
-}
-
-template <int C, int S>
-PCD_HD void passA_body(const PassArgs& a, int bx, int n, int ez, float* smem) {
-    const EdgeF& e = a.e[ez];
-    Geo g;
-    g.n = n; g.TH = a.TH; g.TW = a.TW; g.Ho = a.Ho; g.Wo = a.Wo;
-    g.oy0 = (bx / a.tiles_x) * a.TH;
-    g.ox0 = (bx % a.tiles_x) * a.TW;
-    const int TH = a.TH, TW = a.TW, NPIX = TH * TW, NSTRIP = NPIX / 4, PW4 = TW / 4;
-    const int IH = S * TH + 8, IW = S * TW + 8;
-    const int iy0 = S * g.oy0 - 4, ix0 = S * g.ox0 - 4;
-    float* XIN = smem;
-    float* T = XIN + C * IH * IW;
-    float* P = T + C * NPIX;
-    float* P2 = P + C * NPIX;
-    const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
-    const float* xg = e.x + (long long)n * e.x_ns;
-
-    PCD_FOR(i, C * IH * IW) {
-        const int ch = i / (IH * IW), r = (i / IW) % IH, col = i % IW;
-        const int gy = iy0 + r, gx = ix0 + col;
-        float v = 0.f;
-        if (gy >= 0 && gy < a.Hs && gx >= 0 && gx < a.Ws) v = xg[((long long)ch * a.Hs + gy) * a.Ws + gx];
-        XIN[i] = v;
-    }
-    PCD_SYNC();
-
-    // ---- 3x3 max / avg pool (operations.py:6-7), stride S, pad 1, count_include_pad=False --------
-    PCD_FOR(task, C * NSTRIP) {
-        const int ch = task / NSTRIP, strip = task - ch * NSTRIP;
-        const int oyl = strip / PW4, oxl = (strip - oyl * PW4) * 4;
-        const float* pl = XIN + ch * IH * IW;
-        float mx[4], av[4];
-        float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
-        const int oy = g.oy0 + oyl;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ox = g.ox0 + oxl + j;
-            float m = -INFINITY, s = 0.f;
-            int cnt = 0;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int gy = S * oy + dy - 1, gx = S * ox + dx - 1;
-                    if (gy >= 0 && gy < a.Hs && gx >= 0 && gx < a.Ws) {
-                        const float v = pl[(S * oyl + dy + 3) * IW + S * (oxl + j) + dx + 3];
-                        m = v > m ? v : m;
-                        s += v;
-                        ++cnt;
-                    }
-                }
-            mx[j] = cnt ? m : 0.f;
-            av[j] = cnt ? s / (float)cnt : 0.f;
-            if (oy < a.Ho && ox < a.Wo) {
-                s1 += mx[j]; q1 = fmaf(mx[j], mx[j], q1);
-                s2 += av[j]; q2 = fmaf(av[j], av[j], q2);
-            }
-        }
-        store4(e.saved + slot_p1() * nslot, g, C, ch, oy, g.ox0 + oxl, mx);
-        store4(e.saved + slot_p2() * nslot, g, C, ch, oy, g.ox0 + oxl, av);
-        const int NT = C * NSTRIP;
-        P[0 * NT + task] = s1; P[1 * NT + task] = q1; P[2 * NT + task] = s2; P[3 * NT + task] = q2;
-    }
-    reduce_columns(P, P2, 4, C, NSTRIP, C * NSTRIP, [&](int ch, int k, float v) {
-        const int bn = (k < 2) ? bn_p1() : bn_p2();
-        pcd_atomic_add(e.stats + (bn * 2 + (k & 1)) * C + ch, (double)v);
-    });
-
-    // ---- skip_connect at stride 2 = FactorizedReduce (operations.py:90-104) ----------------------
-    if (S == 2) {
-        PCD_FOR(task, C * NSTRIP) {
-            const int co = task / NSTRIP, strip = task - co * NSTRIP;
-            const int oyl = strip / PW4, oxl = (strip - oyl * PW4) * 4;
-            const int off = (co >= C / 2) ? 1 : 0;
-            const float* w = e.par + co * C;
-            float f[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int ci = 0; ci < C; ++ci) {
-                const float* pl = XIN + ci * IH * IW + (2 * oyl + off + 4) * IW + 2 * oxl + off + 4;
-                const float wv = w[ci];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) f[j] = fmaf(wv, relu(pl[2 * j]), f[j]);
-            }
-            const int oy = g.oy0 + oyl, ox = g.ox0 + oxl;
-            store4(e.saved + slot_f() * nslot, g, C, co, oy, ox, f);
-            float s = 0.f, q = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (oy < a.Ho && ox + j < a.Wo) { s += f[j]; q = fmaf(f[j], f[j], q); }
-            const int NT = C * NSTRIP;
-            P[task] = s; P[NT + task] = q;
-        }
-        reduce_columns(P, P2, 2, C, NSTRIP, C * NSTRIP, [&](int ch, int k, float v) {
-            pcd_atomic_add(e.stats + (bn_f() * 2 + k) * C + ch, (double)v);
-        });
-    }
-
-    // ---- A3, A5 (first half of SepConv, operations.py:55-58), D3, D5 (DilConv, :40-43) -----------
-#define PCD_UNIT_A(U, KS, DIL)                                                                        \
-    unit_forward<C, KS, DIL, S, true>(XIN, IH, IW, 4, e.par + edge_dw_off(C, S, U),                   \
-                                      e.par + edge_pw_off(C, S, U), T, P, P2,                         \
-                                      e.saved + slot_t(U) * nslot, e.saved + slot_z(U) * nslot,       \
-                                      e.stats + bn_unit(S, U) * 2 * C, g)
-    PCD_UNIT_A(0, 3, 1);
-    PCD_UNIT_A(2, 5, 1);
-    PCD_UNIT_A(4, 3, 2);
-    PCD_UNIT_A(5, 5, 2);
-#undef PCD_UNIT_A
-}
-
-PCD_HOSTDEV size_t passB_smem_floats(int C, int TH, int TW) {
-    return (size_t)C * (TH + 8) * (TW + 8) + (size_t)C * TH * TW * 2 + 4 * C * 32 + 2 * C + 64;
-}
-
-// second half of SepConv: BN -> ReLU -> dw (stride 1) -> pw   (operations.py:58-62)
-template <int C>
-PCD_HD void passB_body(const PassArgs& a, int bx, int n, int ez, float* smem) {
-    const EdgeF& e = a.e[ez];
-    Geo g;
-    g.n = n; g.TH = a.TH; g.TW = a.TW; g.Ho = a.Ho; g.Wo = a.Wo;
-    g.oy0 = (bx / a.tiles_x) * a.TH;
-    g.ox0 = (bx % a.tiles_x) * a.TW;
-    const int TH = a.TH, TW = a.TW, NPIX = TH * TW;
-    const int IH = TH + 8, IW = TW + 8;
-    float* Q = smem;
-    float* T = Q + C * IH * IW;
-    float* P = T + C * NPIX;
-    float* P2 = P + C * NPIX;
-    float* BNC = P2 + 4 * C * 32;
-    const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
-    const double cnt = (double)a.B * a.Ho * a.Wo;
-    const int S = a.S;
-    for (int half = 0; half < 2; ++half) {
-        const int uA = half ? 2 : 0, uB = uA + 1;
-        PCD_FOR(j, C) {
-            BnC b = bn_consts(e.stats, C, bn_unit(S, uA), j, cnt, a.eps);
-            BNC[2 * j] = b.mean;
-            BNC[2 * j + 1] = b.rstd;
-        }
-        PCD_SYNC();
-        const float* zA = e.saved + slot_z(uA) * nslot;
-        PCD_FOR(i, C * IH * IW) {
-            const int ch = i / (IH * IW), r = (i / IW) % IH, col = i % IW;
-            const int gy = g.oy0 - 4 + r, gx = g.ox0 - 4 + col;
-            float v = 0.f;
-            if (gy >= 0 && gy < a.Ho && gx >= 0 && gx < a.Wo)
-                v = relu((zA[(((long long)n * C + ch) * a.Ho + gy) * a.Wo + gx] - BNC[2 * ch]) * BNC[2 * ch + 1]);
-            Q[i] = v;
-        }
-        PCD_SYNC();
-        if (half == 0)
-            unit_forward<C, 3, 1, 1, false>(Q, IH, IW, 4, e.par + edge_dw_off(C, S, uB), e.par + edge_pw_off(C, S, uB),
-                                            T, P, P2, e.saved + slot_t(uB) * nslot, e.saved + slot_z(uB) * nslot,
-                                            e.stats + bn_unit(S, uB) * 2 * C, g);
-        else
-            unit_forward<C, 5, 1, 1, false>(Q, IH, IW, 4, e.par + edge_dw_off(C, S, uB), e.par + edge_pw_off(C, S, uB),
-                                            T, P, P2, e.saved + slot_t(uB) * nslot, e.saved + slot_z(uB) * nslot,
-                                            e.stats + bn_unit(S, uB) * 2 * C, g);
-    }
-}
 
 // ---- node combine ---------------------------------------------------------------------------------
 struct EdgeC {

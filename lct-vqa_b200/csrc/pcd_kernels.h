@@ -1,0 +1,13 @@
+// pcd_kernels.h — host launchers of the edge kernels; each lives in its own translation unit so the
+// heavy template instantiations compile in parallel.
+#pragma once
+#include "pcd_edge.cuh"
+
+namespace pcd {
+// `fast` selects the compile-time-tile specialisation for (c, S, a.TH, a.TW); caller guarantees its preconditions.
+bool edge_tile_is_fixed(int c, int S, int TH, int TW, bool stageB);
+int launch_fwdA(const PassArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
+int launch_fwdB(const PassArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
+int launch_bwdA(const EdgeBwdArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
+int launch_bwdB(const EdgeBwdArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
+}  // namespace pcd

@@ -27,6 +27,12 @@ def test_cell_emulated(name, cpp, cp, C, red, rp):
     P.cell_case(name, cpp, cp, C, red, rp, "cpu")
 
 
+# production tile geometries (compile-time-tile "FAST" specialisations), one image each
+@pytest.mark.parametrize("C,stride,B,H", [(16, 1, 1, 64), (32, 2, 1, 64), (32, 1, 2, 32), (64, 2, 1, 32), (64, 1, 2, 16)])
+def test_mixed_op_fixed_tiles_emulated(C, stride, B, H):
+    P.mixed_vs_oracle(C, stride, B, H, "cpu")
+
+
 def test_network_emulated():
     P.network_case("cpu")
 
