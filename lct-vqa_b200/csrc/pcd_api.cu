@@ -5,6 +5,7 @@
 // where every kernel body runs as nested host loops over (block, task): test infrastructure for the index
 // arithmetic, never a product path (pcd_is_cuda_build() returns 0 there and the product loader refuses it).
 #include "pcd_bwd.cuh"
+#include "pcd_pre.cuh"
 #include "pcd_kernels.h"
 #include "pcd_launch.cuh"
 
@@ -39,7 +40,6 @@ static int zero_async(void* p, size_t bytes, void* stream) {
 
 // ---- kernel body adaptors -----------------------------------------------------------------------------
 template <int C> struct KCombine { static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
-struct KPreConv { static const char* name() { return "PreConv"; } static PCD_D void run(const PreArgs& a, int x, int y, int, float* sm) { pre_conv_body(a, x, y, sm); } };
 struct KNorm { static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
 struct KStem { static const char* name() { return "Stem"; } static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
 struct KGapF { static const char* name() { return "GapF"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };
@@ -49,7 +49,6 @@ template <int C> struct KNodeStats { static const char* name() { return C == 4 ?
 struct KSourceGrad { static const char* name() { return "SourceGrad"; } static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
 struct KArchGrads { static const char* name() { return "ArchGrads"; } static PCD_D void run(const ArchGradArgs& a, int, int, int, float*) { arch_grads_body(a); } };
 struct KBnBwdStats { static const char* name() { return "BnBwdStats"; } static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
-struct KPreBwd { static const char* name() { return "PreBwd"; } static PCD_D void run(const PreBwdArgs& a, int x, int, int, float* sm) { pre_bwd_body(a, x, a.nblocks_launch, sm); } };
 struct KStemBwd { static const char* name() { return "StemBwd"; } static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd_body(a, x, a.nblocks_launch, sm); } };
 
 #define PCD_DISPATCH_C(c, EXPR)                         \
@@ -148,7 +147,7 @@ static int run_source_grad(const SourceGradArgs& a, void* stream) {
 // ---- preprocess ------------------------------------------------------------------------------------------
 static int run_pre_forward(int B, int Cin, int Cout, int Hin, int Win, int fr, float eps, float mom, const float* x,
                            const float* w, float* y, double* stats, float* running, long long* nbt, void* stream) {
-    if (Cout % kPreCog) return PCD_ERR_UNSUPPORTED;
+    if (Cout != 16 && Cout != 32 && Cout != 64) return PCD_ERR_UNSUPPORTED;
     if (fr && ((Hin | Win) & 1)) return PCD_ERR_UNSUPPORTED;
     PreArgs a;
     memset(&a, 0, sizeof a);
@@ -156,7 +155,7 @@ static int run_pre_forward(int B, int Cin, int Cout, int Hin, int Win, int fr, f
     a.Ho = fr ? Hin / 2 : Hin; a.Wo = fr ? Win / 2 : Win;
     a.eps = eps; a.momentum = mom; a.x = x; a.w = w; a.y = y; a.stats = stats; a.running = running; a.nbt = nbt;
     const int HW = a.Ho * a.Wo;
-    PCD_TRY((launch<KPreConv, PreArgs>(a, (HW + kPrePx - 1) / kPrePx, B, 1, pre_smem_floats(Cin, Cout), stream)));
+    PCD_TRY(launch_pre_conv(a, stream));
     NormArgs nrm;
     memset(&nrm, 0, sizeof nrm);
     nrm.B = B; nrm.C = Cout; nrm.HW = HW; nrm.eps = eps; nrm.momentum = mom; nrm.src = y; nrm.dst = y;
@@ -176,11 +175,8 @@ static int run_pre_backward(int B, int Cin, int Cout, int Hin, int Win, int fr, 
     PreBwdArgs a;
     memset(&a, 0, sizeof a);
     a.B = B; a.Cin = Cin; a.Cout = Cout; a.Hin = Hin; a.Win = Win; a.Ho = Ho; a.Wo = Wo; a.fr = fr;
-    a.PXB = (Cin >= 128) ? 32 : 64;
-    a.nblocks_px = B * ((HW + a.PXB - 1) / a.PXB);
-    a.nblocks_launch = a.nblocks_px < 296 ? a.nblocks_px : 296;
     a.x = x; a.w = w; a.y = y; a.dy = dy; a.stats = stats; a.bstats = bstats; a.eps = eps; a.dx = dx; a.gw = gw;
-    return launch<KPreBwd, PreBwdArgs>(a, a.nblocks_launch, 1, 1, pre_bwd_smem_floats(Cin, Cout, a.PXB, fr), stream);
+    return launch_pre_bwd(a, stream);
 }
 
 // ---- cell layout -------------------------------------------------------------------------------------------

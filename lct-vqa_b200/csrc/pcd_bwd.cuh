@@ -45,6 +45,57 @@ PCD_HD void node_stats_body(const NodeStatsArgs& a, int bx, int n, int ez, float
     const float* dnb = a.dn + (long long)n * a.dn_ns;
     const float* xb = e.x + (long long)n * e.x_ns;
     const int s = e.stride;
+    const bool vec = (HW % 4 == 0) && (PXB % 4 == 0) && ((((uintptr_t)a.dn) | ((uintptr_t)e.x) | ((uintptr_t)e.saved)) & 15) == 0 &&
+                     a.dn_ns % 4 == 0 && e.x_ns % 4 == 0 && (s == 1 || (a.Wo % 4 == 0 && e.Ws % 4 == 0));
+    if (vec) {
+        PCD_FOR(task, NT) {
+            const int j = task / NSTRIP, strip = task - j * NSTRIP;
+            float acc[kStatK];
+#pragma unroll
+            for (int k = 0; k < kStatK; ++k) acc[k] = 0.f;
+            const int p = p0 + strip * 4;
+            if (p < HW) {
+                const int slots[6] = {slot_p1(), slot_p2(), slot_z(1), slot_z(3), slot_z(4), slot_z(5)};
+                const F4 h4 = *reinterpret_cast<const F4*>(dnb + (long long)(4 * j) * HW + p);
+                const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+                const float* sv = e.saved + ((long long)n * C + j) * HW + p;
+                acc[0] = (h[0] + h[1]) + (h[2] + h[3]);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const F4 v = *reinterpret_cast<const F4*>(sv + slots[k] * nslot);
+                    acc[1 + k] = fmaf(h[0], v.x, fmaf(h[1], v.y, fmaf(h[2], v.z, h[3] * v.w)));
+                }
+                if (s == 1) {
+                    const F4 v = *reinterpret_cast<const F4*>(xb + (long long)j * HW + p);
+                    acc[7] = fmaf(h[0], v.x, fmaf(h[1], v.y, fmaf(h[2], v.z, h[3] * v.w)));
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) {
+                        const F4 d = *reinterpret_cast<const F4*>(dnb + (long long)(4 * j + q) * HW + p);
+                        const F4 b = *reinterpret_cast<const F4*>(xb + (long long)(q * C + j) * HW + p);
+                        acc[8] += fmaf(d.x, b.x, fmaf(d.y, b.y, fmaf(d.z, b.z, d.w * b.w)));
+                    }
+                } else {
+                    const F4 v = *reinterpret_cast<const F4*>(sv + slot_f() * nslot);
+                    acc[7] = fmaf(h[0], v.x, fmaf(h[1], v.y, fmaf(h[2], v.z, h[3] * v.w)));
+                    const int oy = p / a.Wo, ox = p - oy * a.Wo;
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) {
+                        const F4 d = *reinterpret_cast<const F4*>(dnb + (long long)(4 * j + q) * HW + p);
+                        const float* pl = xb + (long long)(q * C + j) * e.Hs * e.Ws + (long long)(2 * oy) * e.Ws + 2 * ox;
+                        const F4 r0a = *reinterpret_cast<const F4*>(pl), r0b = *reinterpret_cast<const F4*>(pl + 4);
+                        const F4 r1a = *reinterpret_cast<const F4*>(pl + e.Ws), r1b = *reinterpret_cast<const F4*>(pl + e.Ws + 4);
+                        const float w0 = fmaxf(fmaxf(r0a.x, r0a.y), fmaxf(r1a.x, r1a.y));
+                        const float w1 = fmaxf(fmaxf(r0a.z, r0a.w), fmaxf(r1a.z, r1a.w));
+                        const float w2 = fmaxf(fmaxf(r0b.x, r0b.y), fmaxf(r1b.x, r1b.y));
+                        const float w3 = fmaxf(fmaxf(r0b.z, r0b.w), fmaxf(r1b.z, r1b.w));
+                        acc[8] += fmaf(d.x, w0, fmaf(d.y, w1, fmaf(d.z, w2, d.w * w3)));
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kStatK; ++k) P[k * NT + task] = acc[k];
+        }
+    } else
     PCD_FOR(task, NT) {
         const int j = task / NSTRIP, strip = task - j * NSTRIP;
         float acc[kStatK];
@@ -154,6 +205,47 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int n) {
                 v.y += (xv.y > 0.f ? m.y : 0.f) + p4.y + p5.y;
                 v.z += (xv.z > 0.f ? m.z : 0.f) + p4.z + p5.z;
                 v.w += (xv.w > 0.f ? m.w : 0.f) + p4.w + p5.w;
+            }
+            *reinterpret_cast<F4*>(ob + p) = v;
+        }
+        return;
+    }
+    bool vecb = vec && ch >= c && a.Ws % 4 == 0;
+    for (int k = 0; k < a.nedges; ++k)
+        vecb = vecb && ((((uintptr_t)a.e[k].dn) & 15) == 0) && a.e[k].dn_ns % 4 == 0 && (a.e[k].stride == 1 || a.Ws % 8 == 0);
+    if (vecb) {
+        const int q = ch / c, j = ch - q * c;
+        PCD_FOR(i4, npx / 4) {
+            const int p = p0 + i4 * 4;
+            F4 v = {0.f, 0.f, 0.f, 0.f};
+            if (a.g0) v = *reinterpret_cast<const F4*>(a.g0 + (long long)n * a.g0_ns + (long long)ch * HW + p);
+            for (int k = 0; k < a.nedges; ++k) {
+                const SrcEdge& e = a.e[k];
+                const float beta = e.beta ? e.beta[0] : 1.f;
+                if (e.stride == 1) {
+                    const F4 d = *reinterpret_cast<const F4*>(e.dn + (long long)n * e.dn_ns + (long long)(4 * j + q) * HW + p);
+                    v.x = fmaf(beta, d.x, v.x); v.y = fmaf(beta, d.y, v.y); v.z = fmaf(beta, d.z, v.z); v.w = fmaf(beta, d.w, v.w);
+                } else {
+                    const int y = p / a.Ws, x = p - y * a.Ws;           // x is a multiple of 4: two 2x2 windows
+                    const int oy = y >> 1, ox = x >> 1, Ho = a.Hs >> 1, Wo = a.Ws >> 1;
+                    const float* pl = xb + (long long)(2 * oy) * a.Ws + x;
+                    const F4 r0 = *reinterpret_cast<const F4*>(pl), r1 = *reinterpret_cast<const F4*>(pl + a.Ws);
+                    const float* dp = e.dn + (long long)n * e.dn_ns + ((long long)(4 * j + q) * Ho + oy) * Wo + ox;
+                    const float d0 = dp[0], d1 = dp[1];
+                    const float w0[4] = {r0.x, r0.y, r1.x, r1.y}, w1[4] = {r0.z, r0.w, r1.z, r1.w};
+                    int b0 = 0, b1 = 0;
+                    float m0 = w0[0], m1 = w1[0];
+#pragma unroll
+                    for (int t = 1; t < 4; ++t) {
+                        if (w0[t] > m0) { m0 = w0[t]; b0 = t; }
+                        if (w1[t] > m1) { m1 = w1[t]; b1 = t; }
+                    }
+                    const int row = (y & 1) * 2;
+                    if (b0 == row) v.x = fmaf(beta, d0, v.x);
+                    if (b0 == row + 1) v.y = fmaf(beta, d0, v.y);
+                    if (b1 == row) v.z = fmaf(beta, d1, v.z);
+                    if (b1 == row + 1) v.w = fmaf(beta, d1, v.w);
+                }
             }
             *reinterpret_cast<F4*>(ob + p) = v;
         }
@@ -280,126 +372,6 @@ PCD_HD void bn_bwd_stats_body(const BnBwdStatArgs& a, int bx, int ch, int n, flo
     reduce_columns(P, P2, 2, 1, 1024, 1024, [&](int, int k, float v) {
         pcd_atomic_add(a.bstats + k * a.C + ch, (double)v);
     });
-}
-
-struct PreBwdArgs {
-    int B, Cin, Cout, Hin, Win, Ho, Wo, fr, PXB, nblocks_px, nblocks_launch;
-    const float* x;        // cell input (B, Cin, Hin, Win)
-    const float* w;
-    const float* y;        // normalised preprocess output (B, Cout, Ho, Wo)
-    const float* dy;       // its grad
-    const double* stats;   // forward sums (for rstd)
-    const double* bstats;  // sum dy, sum dy*y
-    float eps;
-    float* dx;             // (B, Cin, Hin, Win) written; may be null
-    float* gw;             // [Cout][Cin] accumulated; may be null
-};
-
-PCD_HOSTDEV size_t pre_bwd_smem_floats(int Cin, int Cout, int PXB, int fr) {
-    return (size_t)Cout * Cin + (size_t)Cout * PXB + (size_t)(fr ? 2 : 1) * Cin * PXB + 3 * Cout + 16;
-}
-
-PCD_HD void pre_bwd_body(const PreBwdArgs& a, int bx, int nblk, float* smem) {
-    const int Cin = a.Cin, Cout = a.Cout, PXB = a.PXB, HWo = a.Ho * a.Wo;
-    const long long HWi = (long long)a.Hin * a.Win;
-    float* WACC = smem;
-    float* DZ = WACC + Cout * Cin;
-    float* R = DZ + Cout * PXB;                 // [fr?2:1][Cin][PXB]
-    float* COEF = R + (a.fr ? 2 : 1) * Cin * PXB;
-    const double cnt = (double)a.B * HWo;
-    PCD_FOR(i, Cout * Cin) WACC[i] = 0.f;
-    PCD_FOR(co, Cout) {
-        BnC b = bn_consts(a.stats, Cout, 0, co, cnt, a.eps);
-        COEF[3 * co] = b.rstd;
-        COEF[3 * co + 1] = (float)(a.bstats[co] / cnt);
-        COEF[3 * co + 2] = (float)(a.bstats[Cout + co] / cnt);
-    }
-    PCD_SYNC();
-    const int per_img = (HWo + PXB - 1) / PXB;
-    for (int blk = bx; blk < a.nblocks_px; blk += nblk) {
-        const int n = blk / per_img, p0 = (blk - n * per_img) * PXB;
-        const float* xb = a.x + (long long)n * Cin * HWi;
-        PCD_FOR(i, Cout * PXB) {
-            const int co = i / PXB, t = i - co * PXB, p = p0 + t;
-            float v = 0.f;
-            if (p < HWo) {
-                const long long o = ((long long)n * Cout + co) * HWo + p;
-                v = COEF[3 * co] * (a.dy[o] - COEF[3 * co + 1] - a.y[o] * COEF[3 * co + 2]);
-            }
-            DZ[i] = v;
-        }
-        PCD_FOR(i, Cin * PXB) {
-            const int ci = i / PXB, t = i - ci * PXB, p = p0 + t;
-            float v0 = 0.f, v1 = 0.f;
-            if (p < HWo) {
-                if (a.fr) {
-                    const int oy = p / a.Wo, ox = p - oy * a.Wo;
-                    v0 = relu(xb[ci * HWi + (long long)(2 * oy) * a.Win + 2 * ox]);
-                    v1 = relu(xb[ci * HWi + (long long)(2 * oy + 1) * a.Win + 2 * ox + 1]);
-                } else {
-                    v0 = relu(xb[ci * HWi + p]);
-                }
-            }
-            R[i] = v0;
-            if (a.fr) R[Cin * PXB + i] = v1;
-        }
-        PCD_SYNC();
-        if (a.gw) {
-            const int ncig = Cin / 4;
-            PCD_FOR(task, (Cout / 4) * ncig) {
-                const int co0 = (task / ncig) * 4, ci0 = (task % ncig) * 4;
-                const float* Rr = R + ((a.fr && co0 >= Cout / 2) ? Cin * PXB : 0);
-                float acc[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
-                for (int t = 0; t < PXB; ++t) {
-                    float rv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) rv[k] = Rr[(ci0 + k) * PXB + t];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float d = DZ[(co0 + i) * PXB + t];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(d, rv[k], acc[i][k]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) WACC[(co0 + i) * Cin + ci0 + k] += acc[i][k];
-            }
-        }
-        if (a.dx) {
-            float* dxb = a.dx + (long long)n * Cin * HWi;
-            PCD_FOR(i, Cin * PXB) {
-                const int ci = i / PXB, t = i - ci * PXB, p = p0 + t;
-                if (p >= HWo) continue;
-                if (!a.fr) {
-                    float s = 0.f;
-                    for (int co = 0; co < Cout; ++co) s = fmaf(a.w[co * Cin + ci], DZ[co * PXB + t], s);
-                    dxb[ci * HWi + p] = R[i] > 0.f ? s : 0.f;
-                } else {
-                    float s0 = 0.f, s1 = 0.f;
-                    for (int co = 0; co < Cout / 2; ++co) {
-                        s0 = fmaf(a.w[co * Cin + ci], DZ[co * PXB + t], s0);
-                        s1 = fmaf(a.w[(co + Cout / 2) * Cin + ci], DZ[(co + Cout / 2) * PXB + t], s1);
-                    }
-                    const int oy = p / a.Wo, ox = p - oy * a.Wo;
-                    float* d = dxb + ci * HWi + (long long)(2 * oy) * a.Win + 2 * ox;
-                    d[0] = R[i] > 0.f ? s0 : 0.f;
-                    d[1] = 0.f;
-                    d[a.Win] = 0.f;
-                    d[a.Win + 1] = R[Cin * PXB + i] > 0.f ? s1 : 0.f;
-                }
-            }
-        }
-        PCD_SYNC();
-    }
-    if (a.gw) {
-        PCD_FOR(i, Cout * Cin) pcd_atomic_add(a.gw + i, WACC[i]);
-    }
 }
 
 // ---- stem backward ---------------------------------------------------------------------------------------

@@ -76,6 +76,78 @@ PCD_HD void combine_body(const CombineArgs& a, int bx, int n, float* smem) {
     const int npx = (HW - p0) < kCombinePx ? (HW - p0) : kCombinePx;
     const int nstrip = (npx + 3) / 4;
     const long long nslot = (long long)a.B * C * HW;
+    bool vec = (HW % 4 == 0) && ((((uintptr_t)a.out) & 15) == 0) && (a.out_ns % 4 == 0);
+    for (int ei = 0; ei < a.nin; ++ei)
+        vec = vec && ((((uintptr_t)a.e[ei].x) | ((uintptr_t)a.e[ei].saved)) & 15) == 0 && a.e[ei].x_ns % 4 == 0 &&
+              (a.e[ei].stride == 1 || (a.Wo % 4 == 0 && a.e[ei].Ws % 4 == 0));
+    if (vec) {
+        PCD_FOR(task, C * nstrip) {
+            const int j = task / nstrip, strip = task - j * nstrip;
+            const int p = p0 + strip * 4;
+            float m[4] = {0.f, 0.f, 0.f, 0.f}, by[3][4];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) by[q][t] = 0.f;
+            for (int ei = 0; ei < a.nin; ++ei) {
+                const EdgeC& e = a.e[ei];
+                const float* co = COEF + ei * 8 * C;
+                const float beta = e.beta ? e.beta[0] : 1.f;
+                const float* sv = e.saved + ((long long)n * C + j) * HW + p;
+                const float* xb = e.x + (long long)n * e.x_ns;
+                const int slots[6] = {slot_p1(), slot_p2(), slot_z(1), slot_z(3), slot_z(4), slot_z(5)};
+                float acc[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[t] = co[7 * C + j];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const F4 v = *reinterpret_cast<const F4*>(sv + slots[k] * nslot);
+                    const float c = co[k * C + j];
+                    acc[0] = fmaf(c, v.x, acc[0]); acc[1] = fmaf(c, v.y, acc[1]);
+                    acc[2] = fmaf(c, v.z, acc[2]); acc[3] = fmaf(c, v.w, acc[3]);
+                }
+                const float c6 = co[6 * C + j];
+                if (e.stride == 1) {
+                    const F4 v = *reinterpret_cast<const F4*>(xb + (long long)j * HW + p);
+                    acc[0] = fmaf(c6, v.x, acc[0]); acc[1] = fmaf(c6, v.y, acc[1]);
+                    acc[2] = fmaf(c6, v.z, acc[2]); acc[3] = fmaf(c6, v.w, acc[3]);
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) {
+                        const F4 b = *reinterpret_cast<const F4*>(xb + (long long)(q * C + j) * HW + p);
+                        by[q - 1][0] = fmaf(beta, b.x, by[q - 1][0]); by[q - 1][1] = fmaf(beta, b.y, by[q - 1][1]);
+                        by[q - 1][2] = fmaf(beta, b.z, by[q - 1][2]); by[q - 1][3] = fmaf(beta, b.w, by[q - 1][3]);
+                    }
+                } else {
+                    const F4 v = *reinterpret_cast<const F4*>(sv + slot_f() * nslot);
+                    acc[0] = fmaf(c6, v.x, acc[0]); acc[1] = fmaf(c6, v.y, acc[1]);
+                    acc[2] = fmaf(c6, v.z, acc[2]); acc[3] = fmaf(c6, v.w, acc[3]);
+                    const int oy = p / a.Wo, ox = p - oy * a.Wo;
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) {
+                        const float* pl = xb + (long long)(q * C + j) * e.Hs * e.Ws + (long long)(2 * oy) * e.Ws + 2 * ox;
+                        const F4 r0a = *reinterpret_cast<const F4*>(pl), r0b = *reinterpret_cast<const F4*>(pl + 4);
+                        const F4 r1a = *reinterpret_cast<const F4*>(pl + e.Ws), r1b = *reinterpret_cast<const F4*>(pl + e.Ws + 4);
+                        const float w0 = fmaxf(fmaxf(r0a.x, r0a.y), fmaxf(r1a.x, r1a.y));
+                        const float w1 = fmaxf(fmaxf(r0a.z, r0a.w), fmaxf(r1a.z, r1a.w));
+                        const float w2 = fmaxf(fmaxf(r0b.x, r0b.y), fmaxf(r1b.x, r1b.y));
+                        const float w3 = fmaxf(fmaxf(r0b.z, r0b.w), fmaxf(r1b.z, r1b.w));
+                        by[q - 1][0] = fmaf(beta, w0, by[q - 1][0]); by[q - 1][1] = fmaf(beta, w1, by[q - 1][1]);
+                        by[q - 1][2] = fmaf(beta, w2, by[q - 1][2]); by[q - 1][3] = fmaf(beta, w3, by[q - 1][3]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) m[t] += acc[t];
+            }
+            float* ob = a.out + (long long)n * a.out_ns + p;
+            F4 o = {m[0], m[1], m[2], m[3]};
+            *reinterpret_cast<F4*>(ob + (long long)(4 * j) * HW) = o;
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+                F4 b = {by[q - 1][0], by[q - 1][1], by[q - 1][2], by[q - 1][3]};
+                *reinterpret_cast<F4*>(ob + (long long)(4 * j + q) * HW) = b;
+            }
+        }
+    } else
     PCD_FOR(task, C * nstrip) {
         const int j = task / nstrip, strip = task - j * nstrip;
         const int p = p0 + strip * 4;
@@ -139,92 +211,6 @@ PCD_HD void combine_body(const CombineArgs& a, int bx, int n, float* smem) {
             if (bn < edge_nbn(a.e[ei].stride)) a.e[ei].nbt[bn] += 1;
         }
     }
-}
-
-// ---- preprocess: ReLU -> 1x1 conv (ReLUConvBN operations.py:22-33) or FactorizedReduce (:90-104) ----
-struct PreArgs {
-    int B, Cin, Cout, Hin, Win, Ho, Wo, fr;   // fr: 1 => FactorizedReduce (Ho = Hin/2)
-    float eps, momentum;
-    const float* x;      // (B, Cin, Hin, Win) contiguous
-    const float* w;      // RCB: [Cout][Cin]; FR: conv_1 [Cout/2][Cin] then conv_2 [Cout/2][Cin]
-    float* y;            // (B, Cout, Ho, Wo): conv output, normalised in place by pre_norm
-    double* stats;       // sum[Cout], sumsq[Cout]
-    float* running;
-    long long* nbt;
-};
-
-constexpr int kPrePx = 512;     // pixels per block
-constexpr int kPreCog = 8;      // output channels per task
-
-PCD_HOSTDEV size_t pre_smem_floats(int Cin, int Cout) {
-    return (size_t)Cin * Cout + (size_t)16 * (Cout / kPreCog) * (kPrePx / 4) + 16 * (Cout / kPreCog) * 32 + 16;
-}
-
-PCD_HD void pre_conv_body(const PreArgs& a, int bx, int n, float* smem) {
-    const int Cin = a.Cin, Cout = a.Cout, HW = a.Ho * a.Wo, NCG = Cout / kPreCog;
-    float* W = smem;
-    float* P = W + Cin * Cout;
-    const int p0 = bx * kPrePx;
-    const int npx = (HW - p0) < kPrePx ? (HW - p0) : kPrePx;
-    const int nstrip = (npx + 3) / 4, NSTRIPMAX = kPrePx / 4;
-    float* P2 = P + 16 * NCG * NSTRIPMAX;
-    PCD_FOR(i, Cin * Cout) W[i] = a.w[i];
-    PCD_SYNC();
-    const float* xb = a.x + (long long)n * Cin * a.Hin * a.Win;
-    const int NT = NCG * NSTRIPMAX;
-    PCD_FOR(task, NCG * NSTRIPMAX) {
-        const int cg = task / NSTRIPMAX, strip = task - cg * NSTRIPMAX;
-        float acc[kPreCog][4];
-#pragma unroll
-        for (int i = 0; i < kPreCog; ++i)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) acc[i][t] = 0.f;
-        const int p = p0 + strip * 4;
-        if (strip < nstrip) {
-            long long off[4];
-            const int shift = (a.fr && cg * kPreCog >= Cout / 2) ? 1 : 0;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int pp = (p + t < HW) ? p + t : HW - 1;
-                if (a.fr) {
-                    const int oy = pp / a.Wo, ox = pp - oy * a.Wo;
-                    off[t] = (long long)(2 * oy + shift) * a.Win + 2 * ox + shift;
-                } else {
-                    off[t] = pp;
-                }
-            }
-            const long long cs = (long long)a.Hin * a.Win;
-            for (int ci = 0; ci < Cin; ++ci) {
-                float v[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) v[t] = relu(xb[ci * cs + off[t]]);
-#pragma unroll
-                for (int i = 0; i < kPreCog; ++i) {
-                    const float w = W[(cg * kPreCog + i) * Cin + ci];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[i][t] = fmaf(w, v[t], acc[i][t]);
-                }
-            }
-            float* yb = a.y + ((long long)n * Cout + cg * kPreCog) * HW;
-#pragma unroll
-            for (int i = 0; i < kPreCog; ++i)
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (p + t < HW) yb[(long long)i * HW + p + t] = acc[i][t];
-        }
-#pragma unroll
-        for (int i = 0; i < kPreCog; ++i) {
-            float s = 0.f, q = 0.f;
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                if (strip < nstrip && p + t < HW) { s += acc[i][t]; q = fmaf(acc[i][t], acc[i][t], q); }
-            P[(2 * i) * NT + task] = s;
-            P[(2 * i + 1) * NT + task] = q;
-        }
-    }
-    reduce_columns(P, P2, 16, NCG, NSTRIPMAX, NT, [&](int grp, int k, float v) {
-        pcd_atomic_add(a.stats + (k & 1) * Cout + grp * kPreCog + (k >> 1), (double)v);
-    });
 }
 
 // y = (y - mean) * rstd in place (+ optional affine), running-stat update by block (0,0)

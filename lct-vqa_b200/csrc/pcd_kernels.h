@@ -10,4 +10,8 @@ int launch_fwdA(const PassArgs& a, int c, bool fast, int gx, int gy, int gz, voi
 int launch_fwdB(const PassArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
 int launch_bwdA(const EdgeBwdArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
 int launch_bwdB(const EdgeBwdArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
+struct PreArgs;
+struct PreBwdArgs;
+int launch_pre_conv(const PreArgs& a, void* stream);
+int launch_pre_bwd(const PreBwdArgs& a, void* stream);
 }  // namespace pcd

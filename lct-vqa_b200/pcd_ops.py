@@ -11,8 +11,23 @@ import torch
 
 import pcd_native as N
 
+import os
+
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+# debugging aid: PCD_DEBUG_POISON=1 fills every scratch / output buffer with NaN before the kernels run, so a
+# read of memory the kernels never wrote cannot hide behind stale-but-plausible values
+_POISON = os.environ.get("PCD_DEBUG_POISON", "0") == "1"
+
+
+def _empty(shape, dtype, device):
+    if _POISON and dtype in (torch.float32, torch.float64):
+        return torch.full(shape if isinstance(shape, tuple) else (shape,), float("nan"), dtype=dtype, device=device)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def _empty_like(t):
+    return _empty(tuple(t.shape), t.dtype, t.device)
 
 
 # --------------------------------------------------------------------------------------------
@@ -147,9 +162,9 @@ class CellFunction(torch.autograd.Function):
         B, _, H, W = s1c.shape
         sz = handle.sizes(lib, B, H, W)
         dev = s1c.device
-        out = torch.empty((B, 4 * handle.cfg[2], sz.out_height, sz.out_width), dtype=torch.float32, device=dev)
-        saved = torch.empty(sz.saved_floats, dtype=torch.float32, device=dev)
-        stats = torch.empty(sz.stats_doubles, dtype=torch.float64, device=dev)
+        out = _empty((B, 4 * handle.cfg[2], sz.out_height, sz.out_width), torch.float32, dev)
+        saved = _empty(sz.saved_floats, torch.float32, dev)
+        stats = _empty(sz.stats_doubles, torch.float64, dev)
         a = N.CellFwdArgs(handle.shape(B, H, W), N.ptr(s0c), N.ptr(s1c), N.ptr(w), N.ptr(w2), handle.param_ptr,
                           handle.running_ptr, handle.nbt_ptr, N.ptr(out), N.ptr(saved), N.ptr(stats))
         N.check(lib, lib.pcd_cell_forward(C.byref(a), N.stream_for(s1c)), "pcd_cell_forward")
@@ -168,13 +183,13 @@ class CellFunction(torch.autograd.Function):
         gout = _f32c(gout)
         need_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_par = any(ctx.needs_input_grad[5:])
-        gs0 = torch.empty_like(s0) if need_in else None
-        gs1 = torch.empty_like(s1) if need_in else None
-        gw = torch.empty_like(w)
-        gw2 = torch.empty_like(w2)
-        gpar = torch.empty(sz.param_floats, dtype=torch.float32, device=dev) if need_par else None
-        work = torch.empty(sz.bwd_work_floats, dtype=torch.float32, device=dev)
-        bstats = torch.empty(sz.bwd_stats_doubles, dtype=torch.float64, device=dev)
+        gs0 = _empty_like(s0) if need_in else None
+        gs1 = _empty_like(s1) if need_in else None
+        gw = _empty_like(w)
+        gw2 = _empty_like(w2)
+        gpar = _empty(sz.param_floats, torch.float32, dev) if need_par else None
+        work = _empty(sz.bwd_work_floats, torch.float32, dev)
+        bstats = _empty(sz.bwd_stats_doubles, torch.float64, dev)
         a = N.CellBwdArgs(handle.shape(B, H, W), N.ptr(s0), N.ptr(s1), N.ptr(w), N.ptr(w2), handle.param_ptr,
                           N.ptr(out), N.ptr(saved), N.ptr(stats), N.ptr(gout), N.ptr(gs0), N.ptr(gs1), N.ptr(gw),
                           N.ptr(gw2), N.ptr(gpar), N.ptr(work), N.ptr(bstats), int(need_par), int(need_in))
@@ -215,9 +230,9 @@ class MixedOpFunction(torch.autograd.Function):
         B, Cc, H, W = xc.shape
         sz = handle.sizes(lib, B, H, W)
         dev = xc.device
-        out = torch.empty((B, Cc, sz.out_height, sz.out_width), dtype=torch.float32, device=dev)
-        saved = torch.empty(sz.saved_floats, dtype=torch.float32, device=dev)
-        stats = torch.empty(sz.stats_doubles, dtype=torch.float64, device=dev)
+        out = _empty((B, Cc, sz.out_height, sz.out_width), torch.float32, dev)
+        saved = _empty(sz.saved_floats, torch.float32, dev)
+        stats = _empty(sz.stats_doubles, torch.float64, dev)
         a = N.MixedFwdArgs(handle.shape(B, H, W), N.ptr(xc), N.ptr(w), handle.param_ptr, handle.running_ptr,
                            handle.nbt_ptr, N.ptr(out), N.ptr(saved), N.ptr(stats))
         N.check(lib, lib.pcd_mixedop_forward(C.byref(a), N.stream_for(xc)), "pcd_mixedop_forward")
@@ -235,11 +250,11 @@ class MixedOpFunction(torch.autograd.Function):
         dev = x.device
         gout = _f32c(gout)
         need_par = any(ctx.needs_input_grad[3:])
-        gx = torch.empty_like(x)
-        gw = torch.empty_like(w)
-        gpar = torch.empty(sz.param_floats, dtype=torch.float32, device=dev) if need_par else None
-        work = torch.empty(sz.bwd_work_floats, dtype=torch.float32, device=dev)
-        bstats = torch.empty(sz.bwd_stats_doubles, dtype=torch.float64, device=dev)
+        gx = _empty_like(x)
+        gw = _empty_like(w)
+        gpar = _empty(sz.param_floats, torch.float32, dev) if need_par else None
+        work = _empty(sz.bwd_work_floats, torch.float32, dev)
+        bstats = _empty(sz.bwd_stats_doubles, torch.float64, dev)
         a = N.MixedBwdArgs(handle.shape(B, H, W), N.ptr(x), N.ptr(w), handle.param_ptr, N.ptr(saved), N.ptr(stats),
                            N.ptr(gout), N.ptr(gx), N.ptr(gw), N.ptr(gpar), N.ptr(work), N.ptr(bstats), int(need_par))
         N.check(lib, lib.pcd_mixedop_backward(C.byref(a), N.stream_for(x)), "pcd_mixedop_backward")
@@ -262,9 +277,9 @@ class StemFunction(torch.autograd.Function):
             raise ValueError("stem expects 3 input channels")
         cout = conv_w.shape[0]
         dev = xc.device
-        out = torch.empty((B, cout, H, W), dtype=torch.float32, device=dev)
-        z = torch.empty_like(out)
-        stats = torch.empty(2 * cout, dtype=torch.float64, device=dev)
+        out = _empty((B, cout, H, W), torch.float32, dev)
+        z = _empty_like(out)
+        stats = _empty(2 * cout, torch.float64, dev)
         a = N.StemArgs(B, cout, H, W, BN_EPS, BN_MOMENTUM, N.ptr(xc), ptrs[0], ptrs[1], ptrs[2], N.ptr(out), N.ptr(z),
                        N.ptr(stats), None, None, None, None)
         N.check(lib, lib.pcd_stem_forward(C.byref(a), N.stream_for(xc)), "pcd_stem_forward")
@@ -284,8 +299,8 @@ class StemFunction(torch.autograd.Function):
         need_par = any(ctx.needs_input_grad[2:])
         if not need_par:
             return (None, None, None, None, None)
-        gpar = torch.empty(cout * 29, dtype=torch.float32, device=x.device)
-        bstats = torch.empty(2 * cout, dtype=torch.float64, device=x.device)
+        gpar = _empty(cout * 29, torch.float32, x.device)
+        bstats = _empty(2 * cout, torch.float64, x.device)
         a = N.StemArgs(B, cout, H, W, BN_EPS, BN_MOMENTUM, N.ptr(x), ctx.ptrs[0], None, None, None, N.ptr(z),
                        N.ptr(stats), N.ptr(gout), None, N.ptr(gpar), N.ptr(bstats))
         N.check(lib, lib.pcd_stem_backward(C.byref(a), N.stream_for(x)), "pcd_stem_backward")
@@ -301,7 +316,7 @@ class AdaptiveAvgPoolFunction(torch.autograd.Function):
         lib = N.lib_for(x)
         xc = _f32c(x)
         B, Cc, H, W = xc.shape
-        y = torch.empty((B, Cc, size, size), dtype=torch.float32, device=xc.device)
+        y = _empty((B, Cc, size, size), torch.float32, xc.device)
         N.check(lib, lib.pcd_adaptive_avgpool_forward(N.ptr(xc), N.ptr(y), B, Cc, H, W, size, size, N.stream_for(xc)),
                 "pcd_adaptive_avgpool_forward")
         ctx.meta = (B, Cc, H, W, size)
@@ -312,7 +327,7 @@ class AdaptiveAvgPoolFunction(torch.autograd.Function):
         B, Cc, H, W, size = ctx.meta
         lib = N.lib_for(gy)
         gy = _f32c(gy)
-        gx = torch.empty((B, Cc, H, W), dtype=torch.float32, device=gy.device)
+        gx = _empty((B, Cc, H, W), torch.float32, gy.device)
         N.check(lib, lib.pcd_adaptive_avgpool_backward(N.ptr(gy), N.ptr(gx), B, Cc, H, W, size, size, N.stream_for(gy)),
                 "pcd_adaptive_avgpool_backward")
         return gx, None
@@ -326,7 +341,7 @@ class ChannelShuffleFunction(torch.autograd.Function):
         lib = N.lib_for(x)
         xc = _f32c(x)
         B, Cc, H, W = xc.shape
-        y = torch.empty_like(xc)
+        y = _empty_like(xc)
         N.check(lib, lib.pcd_channel_shuffle(N.ptr(xc), N.ptr(y), B, Cc, H * W, groups, N.stream_for(xc)),
                 "pcd_channel_shuffle")
         ctx.groups = groups
@@ -337,7 +352,7 @@ class ChannelShuffleFunction(torch.autograd.Function):
         lib = N.lib_for(gy)
         gy = _f32c(gy)
         B, Cc, H, W = gy.shape
-        gx = torch.empty_like(gy)
+        gx = _empty_like(gy)
         # inverse of a (groups, C/groups) transpose is the (C/groups, groups) transpose
         N.check(lib, lib.pcd_channel_shuffle(N.ptr(gy), N.ptr(gx), B, Cc, H * W, Cc // ctx.groups, N.stream_for(gy)),
                 "pcd_channel_shuffle")
@@ -355,8 +370,8 @@ class PreprocessFunction(torch.autograd.Function):
         xc = _f32c(x)
         B, _, H, W = xc.shape
         ho, wo = (H // 2, W // 2) if fr else (H, W)
-        y = torch.empty((B, c_out, ho, wo), dtype=torch.float32, device=xc.device)
-        stats = torch.empty(2 * c_out, dtype=torch.float64, device=xc.device)
+        y = _empty((B, c_out, ho, wo), torch.float32, xc.device)
+        stats = _empty(2 * c_out, torch.float64, xc.device)
         a = N.PreArgs(B, c_in, c_out, H, W, int(fr), BN_EPS, BN_MOMENTUM, N.ptr(xc), ptrs[0], ptrs[1], ptrs[2],
                       N.ptr(y), N.ptr(stats), None, None, None, None)
         N.check(lib, lib.pcd_preprocess_forward(C.byref(a), N.stream_for(xc)), "pcd_preprocess_forward")
@@ -370,10 +385,10 @@ class PreprocessFunction(torch.autograd.Function):
         fr, c_in, c_out, ptrs, B, H, W = ctx.meta
         lib = N.lib_for(x)
         gy = _f32c(gy)
-        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gx = _empty_like(x) if ctx.needs_input_grad[0] else None
         need_w = any(ctx.needs_input_grad[2:])
-        gw = torch.empty(c_out * c_in, dtype=torch.float32, device=x.device) if need_w else None
-        bstats = torch.empty(2 * c_out, dtype=torch.float64, device=x.device)
+        gw = _empty(c_out * c_in, torch.float32, x.device) if need_w else None
+        bstats = _empty(2 * c_out, torch.float64, x.device)
         a = N.PreArgs(B, c_in, c_out, H, W, int(fr), BN_EPS, BN_MOMENTUM, N.ptr(x), ptrs[0], None, None, N.ptr(y),
                       N.ptr(stats), N.ptr(gy), N.ptr(gx), N.ptr(gw), N.ptr(bstats))
         N.check(lib, lib.pcd_preprocess_backward(C.byref(a), N.stream_for(x)), "pcd_preprocess_backward")

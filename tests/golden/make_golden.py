@@ -164,9 +164,20 @@ def vqa_case():
     return npz(out)
 
 
-def architect_case(unrolled):
+def _ulp_noise_(module, seed, frac=0.3):
+    """Move a random 30% of every weight up by one ulp (what fp32 atomic-order noise does on a GPU)."""
+    g = gen(seed)
+    with torch.no_grad():
+        for p in module.parameters():
+            up = torch.nextafter(p, torch.full_like(p, float("inf")))
+            p.copy_(torch.where(torch.rand(p.shape, generator=g) < frac, up, p))
+
+
+def _architect_run(unrolled, seeds, ulp_seed=None):
     m = make_vqa()
     m.dropout.p = 0.0
+    if ulp_seed is not None:
+        _ulp_noise_(m, ulp_seed)
     # model.new() (vqa_model.py:342-349) builds a fresh VqaModel whose Dropout(0.5) is live and whose
     # masks depend on how much RNG the throw-away init consumed; the harness switches it off on the
     # unrolled copy as well (SURVEY.md Appendix C) — no reference code is modified.
@@ -188,10 +199,32 @@ def architect_case(unrolled):
         cap["hvp"] = [r.clone() for r in res]
         return res
     arch._hessian_vector_product = spy
-    tr, va = batch(12), batch(13)
+    tr, va = batch(seeds[0]), batch(seeds[1])
     torch.manual_seed(5)     # model.new() draws from the global RNG for its throw-away init
     arch.step(*tr, *va, 1e-3, None, unrolled=unrolled)
-    out = {}
+    return m, cap
+
+
+def architect_case(unrolled):
+    """Architect.step on a WELL-CONDITIONED point.  The finite-difference HVP evaluates gradients at
+    w +- R v; if an activation there sits on a ReLU / max-pool tie, a one-ulp change of the weights flips the
+    gradient by ~0.3% in the reference itself (observed for batch seeds 12/13).  GPU weight gradients carry
+    one-ulp ordering noise, so the fixture is only accepted when the reference is stable under that noise."""
+    seeds = (12, 13)
+    for attempt in range(20):
+        m, cap = _architect_run(unrolled, seeds)
+        stable = True
+        for ulp_seed in (101, 102, 103, 104):
+            m2, _ = _architect_run(unrolled, seeds, ulp_seed)
+            for a, b in zip(m.arch_parameters(), m2.arch_parameters()):
+                rel = ((a.grad - b.grad).abs().max() / a.grad.abs().max()).item()
+                stable = stable and rel < 2e-5
+        if stable:
+            break
+        seeds = (seeds[0] + 10, seeds[1] + 10)
+    else:
+        raise RuntimeError("no well-conditioned test point found")
+    out = {"seed_train": seeds[0], "seed_valid": seeds[1]}
     for i, a in enumerate(m.arch_parameters()):
         out[f"arch_after{i}"] = a.data
         out[f"darch{i}"] = a.grad

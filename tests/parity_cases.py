@@ -212,7 +212,8 @@ def architect_case(device, unrolled):
     arch = Architect(m, Namespace(arch_learn_rate=6e-4, arch_wt_decay=1e-3, qst_only=False))
     if unrolled:
         arch.unrolled_model().dropout.p = 0.0
-    arch.step(*vqa_batch(12, device), *vqa_batch(13, device), 1e-3, None, unrolled=unrolled)
+    arch.step(*vqa_batch(int(g["seed_train"]), device), *vqa_batch(int(g["seed_valid"]), device), 1e-3, None,
+              unrolled=unrolled)
     for i, a in enumerate(m.arch_parameters()):
         assert_close(a.grad, g[f"darch{i}"], REL_TOL, f"darch{i}")
         assert_close(a.detach(), g[f"arch_after{i}"], 1e-5, f"arch_after{i}")

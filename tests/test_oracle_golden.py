@@ -171,7 +171,8 @@ def test_architect_step(unrolled):
     g = load_golden("architect_unrolled" if unrolled else "architect_first")
     par, buf, arch = vqa_state()
     dbg = {}
-    grads = O.architect_step(par, O.BNState(buf), arch, {}, batch(12), batch(13), 1e-3, list(par.keys()),
+    grads = O.architect_step(par, O.BNState(buf), arch, {}, batch(int(g["seed_train"])), batch(int(g["seed_valid"])),
+                             1e-3, list(par.keys()),
                              unrolled=unrolled, dropout_p=0.0, **({"debug": dbg} if unrolled else {}))
     for i in range(4):
         assert_close(grads[i], g[f"darch{i}"], 1e-4, f"darch{i}")
