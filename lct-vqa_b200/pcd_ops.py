@@ -113,11 +113,42 @@ class Arena:
     def invalidate(self):
         self.valid = False
 
+    def flat(self, which):
+        """One flat tensor aliasing a whole group ('params' | 'running' | 'nbt') of this arena."""
+        group = getattr(self, which)
+        t0 = group[0]
+        n = sum(t.numel() for t in group)
+        return torch.empty(0, dtype=t0.dtype, device=t0.device).set_(t0.untyped_storage(), t0.storage_offset(), (n,))
+
 
 def _views(flat, params):
-    """Split a flat grad arena into per-parameter views (one C++ call + cheap reshapes)."""
-    parts = flat.split_with_sizes([p.numel() for p in params])
-    return [g.view(p.shape) for g, p in zip(parts, params)]
+    """Split a flat grad arena into per-parameter views (a single C++ call)."""
+    return torch._C._nn.unflatten_dense_tensors(flat, params)
+
+
+# Activation-only backward (SURVEY.md §8b): the two finite-difference passes of the Hessian-vector
+# product only need d loss / d alpha,beta (architect_vqa.py:110,115).  autograd's needs_input_grad cannot
+# express that (it mirrors requires_grad, not the targets of autograd.grad), so the architect says so
+# explicitly; the cell kernels then skip every weight-gradient phase and no per-parameter autograd edges
+# are created.
+_WEIGHT_GRADS = [True]
+
+
+class weight_grads:
+    def __init__(self, enabled):
+        self.enabled = enabled
+
+    def __enter__(self):
+        self.prev = _WEIGHT_GRADS[0]
+        _WEIGHT_GRADS[0] = self.enabled
+
+    def __exit__(self, *exc):
+        _WEIGHT_GRADS[0] = self.prev
+        return False
+
+
+def weight_grads_enabled():
+    return _WEIGHT_GRADS[0]
 
 
 def _f32c(t):
@@ -182,7 +213,7 @@ class CellFunction(torch.autograd.Function):
         dev = s1.device
         gout = _f32c(gout)
         need_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        need_par = any(ctx.needs_input_grad[5:])
+        need_par = len(params) > 0 and any(ctx.needs_input_grad[5:])
         gs0 = _empty_like(s0) if need_in else None
         gs1 = _empty_like(s1) if need_in else None
         gw = _empty_like(w)
@@ -249,7 +280,7 @@ class MixedOpFunction(torch.autograd.Function):
         sz = handle.sizes(lib, B, H, W)
         dev = x.device
         gout = _f32c(gout)
-        need_par = any(ctx.needs_input_grad[3:])
+        need_par = len(params) > 0 and any(ctx.needs_input_grad[3:])
         gx = _empty_like(x)
         gw = _empty_like(w)
         gpar = _empty(sz.param_floats, torch.float32, dev) if need_par else None

@@ -19,6 +19,8 @@ Same arithmetic, different mechanics:
 """
 import torch
 
+import pcd_ops
+
 
 def _concat(xs):
     return torch.cat([x.reshape(-1) for x in xs])
@@ -36,12 +38,41 @@ class Architect(object):
                                           betas=(0.5, 0.999), weight_decay=args.arch_wt_decay)
         self.exp_zero_grad = 6 if self.args.qst_only else 0
         self._twin = None
+        self._cache = {}
         self.last = {}            # quantities of the last unrolled step, for inspection / tests
 
     # ---- helpers -----------------------------------------------------------------------------------
     def _allreduce(self, tensors):
         if self.reducer is not None:
             self.reducer(tensors)
+
+    def _lists(self, module):
+        """(parameters, buffers) of a module, cached: walking 700 sub-modules costs milliseconds per call."""
+        key = id(module)
+        if key not in self._cache:
+            self._cache[key] = (list(module.parameters()), list(module.buffers()))
+        return self._cache[key]
+
+    def _copy_state(self, twin, model):
+        """twin <- model (weights, BN buffers, alphas): flat arena copies for the search network."""
+        tp, tb = self._lists(twin)
+        mp, mb = self._lists(model)
+        nets = [(a, b) for a, b in zip(twin.modules(), model.modules()) if hasattr(a, '_arena') and hasattr(b, 'cells')] \
+            if 'nets' not in self._cache else self._cache['nets']
+        self._cache['nets'] = nets
+        covered_p, covered_b = set(), set()
+        for tn, mn in nets[:1]:
+            ta, ma = tn._arena(), mn._arena()
+            for which in ('params', 'running', 'nbt'):
+                ta.flat(which).copy_(ma.flat(which))
+            covered_p.update(id(p) for p in ta.params)
+            covered_b.update(id(b) for b in ta.running + ta.nbt)
+        rest = [(a, b) for a, b in zip(tp, mp) if id(a) not in covered_p] + \
+               [(a, b) for a, b in zip(tb, mb) if id(a) not in covered_b]
+        for a, b in rest:
+            a.copy_(b)
+        for x, y in zip(twin.arch_parameters(), model.arch_parameters()):
+            x.copy_(y)
 
     def unrolled_model(self):
         """The persistent twin that holds w' (created on first use through model.new())."""
@@ -82,25 +113,20 @@ class Architect(object):
 
     def _compute_unrolled_model(self, img, qst, label, eta, network_optimizer):
         model = self.model
-        params = list(model.parameters())
+        params, _ = self._lists(model)
         loss = model._loss(img, qst, label, self.args.qst_only)
         grads = self._calc_grad(loss, params, self.exp_zero_grad)
         self._allreduce(grads)
         twin = self.unrolled_model()
         with torch.no_grad():
-            tparams = list(twin.parameters())
-            torch._foreach_copy_(tparams, params)
-            torch._foreach_add_(tparams, grads, alpha=-eta)              # theta - eta * (0 + dtheta)
-            tb, mb = list(twin.buffers()), list(model.buffers())
-            torch._foreach_copy_(tb, mb)                                 # model_dict carries the live BN buffers
-            for x, y in zip(twin.arch_parameters(), model.arch_parameters()):
-                x.copy_(y)
+            self._copy_state(twin, model)                                # model_dict carries the live BN buffers
+            torch._foreach_add_(self._lists(twin)[0], grads, alpha=-eta)  # theta - eta * (0 + dtheta)
         return twin
 
     def _backward_step_unrolled(self, img_train, qst_train, label_train, img_valid, qst_valid, label_valid,
                                 eta, network_optimizer):
         twin = self._compute_unrolled_model(img_train, qst_train, label_train, eta, network_optimizer)
-        tparams = list(twin.parameters())
+        tparams = self._lists(twin)[0]
         tarch = twin.arch_parameters()
         unrolled_loss = twin._loss(img_valid, qst_valid, label_valid, self.args.qst_only)
         got = torch.autograd.grad(unrolled_loss, list(tarch) + tparams, allow_unused=True)
@@ -116,16 +142,18 @@ class Architect(object):
 
     def _hessian_vector_product(self, vector, img, qst, label, r=1e-2):
         model = self.model
-        params = list(model.parameters())
+        params = self._lists(model)[0]
         arch = model.arch_parameters()
         with torch.no_grad():
             vnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(vector)))
             R = (r / vnorm).item()
             torch._foreach_add_(params, vector, alpha=R)
-        grads_p = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
+        with pcd_ops.weight_grads(False):      # only d/d(alpha, beta) is needed at w +- R v
+            grads_p = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
         with torch.no_grad():
             torch._foreach_add_(params, vector, alpha=-2 * R)
-        grads_n = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
+        with pcd_ops.weight_grads(False):
+            grads_n = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
         with torch.no_grad():
             torch._foreach_add_(params, vector, alpha=R)
         self._allreduce(grads_p + grads_n)

@@ -222,7 +222,12 @@ class Network(_ArenaModule):
         if total != ar.param_floats:
             raise RuntimeError("parameter arena does not match the kernel layout")
         params = ar.params
-        s0 = s1 = pcd_ops.StemFunction.apply(x, (ar.param_ptr, ar.running_ptr, ar.nbt_ptr), *params[:3])
+        wg = pcd_ops.weight_grads_enabled()
+        if wg:
+            s0 = s1 = pcd_ops.StemFunction.apply(x, (ar.param_ptr, ar.running_ptr, ar.nbt_ptr), *params[:3])
+        else:   # activation-only pass: no autograd edges to the weights at all
+            with torch.no_grad():
+                s0 = s1 = pcd_ops.StemFunction.apply(x, (ar.param_ptr, ar.running_ptr, ar.nbt_ptr), *params[:3])
         w_normal = w_reduce = None
         pos = 3
         for cell, (handle, p_off, r_off, n_off, n_par) in zip(self.cells, cells):
@@ -237,7 +242,8 @@ class Network(_ArenaModule):
             handle.param_ptr = ar.param_ptr + 4 * p_off
             handle.running_ptr = ar.running_ptr + 4 * r_off
             handle.nbt_ptr = ar.nbt_ptr + 8 * n_off
-            s0, s1 = s1, pcd_ops.CellFunction.apply(s0, s1, weights, weights2, handle, *params[pos:pos + n_par])
+            cell_params = params[pos:pos + n_par] if wg else ()
+            s0, s1 = s1, pcd_ops.CellFunction.apply(s0, s1, weights, weights2, handle, *cell_params)
             pos += n_par
         out = pcd_ops.AdaptiveAvgPoolFunction.apply(s1, self.output_size)
         return out.flatten(start_dim=1)
