@@ -270,14 +270,14 @@ def run_b200(a):
     # ---- per-launch CUDA-event profile of this library's kernels (separate region: events perturb) ----
     hbm, peak_src = peaks()
     roofline, by_kernel = None, {}
+    nprof = 2
+    lib.pcd_profile_enable(1)              # every rank runs the same steps (they contain collectives)
+    for _ in range(nprof):
+        step_resident()
+    torch.cuda.synchronize()
+    prof = pcd_native.profile_collect(lib)
+    lib.pcd_profile_enable(0)
     if rank == 0:
-        nprof = 2
-        lib.pcd_profile_enable(1)
-        for _ in range(nprof):
-            step_resident()
-        torch.cuda.synchronize()
-        prof = pcd_native.profile_collect(lib)
-        lib.pcd_profile_enable(0)
         total_ms = sum(v[0] for v in prof.values())
         for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             by_kernel[k] = {"ms_per_step": t / nprof, "launches_per_step": c / nprof, "share": t / total_ms}
@@ -297,8 +297,9 @@ def run_b200(a):
 
     extras = {}
     if not a.no_extras:
-        extras["mixedop_fwd_bwd"] = mixedop_microbench(dev, a.batch, hbm)
-        if rank == 0 or world > 1:
+        if rank == 0:
+            extras["mixedop_fwd_bwd"] = mixedop_microbench(dev, a.batch, hbm)
+        if True:
             w_ms = timed(lambda: stepper.w_step(*train), max(3, a.steps // 2)) / max(3, a.steps // 2)
             fo_ms = timed(lambda: stepper.step(train, valid, 1e-3, unrolled=False), max(3, a.steps // 2)) / max(3, a.steps // 2)
             extras["w_step_only_steps_per_s"] = world * 1e3 / w_ms
