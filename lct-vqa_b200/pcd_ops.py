@@ -20,6 +20,9 @@ BN_MOMENTUM = 0.1
 _POISON = os.environ.get("PCD_DEBUG_POISON", "0") == "1"
 
 
+_DEBUG_KEEP = None      # set to a list to retain the buffers of every CellFunction.backward (debugging)
+
+
 def _empty(shape, dtype, device):
     if _POISON and dtype in (torch.float32, torch.float64):
         return torch.full(shape if isinstance(shape, tuple) else (shape,), float("nan"), dtype=dtype, device=device)
@@ -225,6 +228,9 @@ class CellFunction(torch.autograd.Function):
                           N.ptr(out), N.ptr(saved), N.ptr(stats), N.ptr(gout), N.ptr(gs0), N.ptr(gs1), N.ptr(gw),
                           N.ptr(gw2), N.ptr(gpar), N.ptr(work), N.ptr(bstats), int(need_par), int(need_in))
         N.check(lib, lib.pcd_cell_backward(C.byref(a), N.stream_for(s1)), "pcd_cell_backward")
+        if _DEBUG_KEEP is not None:
+            _DEBUG_KEEP.append(dict(cfg=handle.cfg, gout=gout, gs0=gs0, gs1=gs1, work=work, bstats=bstats, gpar=gpar,
+                                    s0=s0, s1=s1, saved=saved, stats=stats, w=w, w2=w2, sizes=sz))
         pg = _views(gpar, params) if need_par else [None] * len(params)
         return (gs0, gs1, gw, gw2, None, *pg)
 

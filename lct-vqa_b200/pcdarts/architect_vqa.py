@@ -39,6 +39,8 @@ class Architect(object):
         self.exp_zero_grad = 6 if self.args.qst_only else 0
         self._twin = None
         self._cache = {}
+        # True: keep R = r/||v|| on the device (no host sync) so the whole step can live in a CUDA graph
+        self.device_scalars = False
         self.last = {}            # quantities of the last unrolled step, for inspection / tests
 
     # ---- helpers -----------------------------------------------------------------------------------
@@ -146,16 +148,27 @@ class Architect(object):
         arch = model.arch_parameters()
         with torch.no_grad():
             vnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(vector)))
-            R = (r / vnorm).item()
-            torch._foreach_add_(params, vector, alpha=R)
+            if self.device_scalars:
+                R = r / vnorm                                        # 0-dim device tensor
+                step_v = torch._foreach_mul(vector, R)               # R * v once; then +1, -2, +1 of it
+                torch._foreach_add_(params, step_v)
+            else:
+                R = (r / vnorm).item()
+                torch._foreach_add_(params, vector, alpha=R)
         with pcd_ops.weight_grads(False):      # only d/d(alpha, beta) is needed at w +- R v
             grads_p = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
         with torch.no_grad():
-            torch._foreach_add_(params, vector, alpha=-2 * R)
+            if self.device_scalars:
+                torch._foreach_add_(params, step_v, alpha=-2.0)
+            else:
+                torch._foreach_add_(params, vector, alpha=-2 * R)
         with pcd_ops.weight_grads(False):
             grads_n = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
         with torch.no_grad():
-            torch._foreach_add_(params, vector, alpha=R)
+            if self.device_scalars:
+                torch._foreach_add_(params, step_v)
+            else:
+                torch._foreach_add_(params, vector, alpha=R)
         self._allreduce(grads_p + grads_n)
         self.last.update(g_pos=grads_p, g_neg=grads_n, R=R, vnorm=vnorm)
         return [(x - y).div_(2 * R) for x, y in zip(grads_p, grads_n)]

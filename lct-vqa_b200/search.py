@@ -39,3 +39,40 @@ class SearchStep:
     def step(self, train_batch, valid_batch, lr, unrolled=True):
         self.alpha_step(train_batch, valid_batch, lr, unrolled)
         return self.w_step(*train_batch)
+
+
+class GraphedSearchStep:
+    """The whole search step (alpha-step + w-step, ~4000 kernel launches and a few thousand torch ops) captured
+    once in a CUDA graph and replayed: the step is otherwise host-bound.  Inputs are copied into static device
+    buffers; the learning rate is baked in at capture (re-capture when the schedule changes it).
+
+    Requirements: optimizers created with capturable=True (Adam keeps its step counter on the device), a
+    single process (no collectives inside the capture), shapes fixed.
+    """
+
+    def __init__(self, step, train_batch, valid_batch, lr, unrolled=True, warmup=3):
+        self.step_obj = step
+        self.lr, self.unrolled = lr, unrolled
+        self.train = [t.clone() for t in train_batch]
+        self.valid = [t.clone() for t in valid_batch]
+        step.architect.device_scalars = True
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up on a side stream (allocator, cuDNN/cuBLAS handles)
+            for _ in range(warmup):
+                step.step(self.train, self.valid, lr, unrolled)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = step.step(self.train, self.valid, lr, unrolled)
+
+    def __call__(self, train_batch=None, valid_batch=None):
+        if train_batch is not None:
+            for dst, src in zip(self.train, train_batch):
+                dst.copy_(src, non_blocking=True)
+        if valid_batch is not None:
+            for dst, src in zip(self.valid, valid_batch):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -46,6 +46,62 @@ def test_w_step_golden():
     P.wstep_case(DEV)
 
 
+def _graph_pair(unrolled):
+    from argparse import Namespace
+    from pcdarts.architect_vqa import Architect
+    from search import GraphedSearchStep, SearchStep
+
+    def make():
+        m = P.make_vqa(DEV)
+        arch = Architect(m, Namespace(arch_learn_rate=0.0, arch_wt_decay=0.0, qst_only=False))
+        arch.optimizer = torch.optim.Adam(m.arch_parameters(), lr=0.0, betas=(0.5, 0.999), capturable=True)
+        arch.unrolled_model().dropout.p = 0.0
+        arch.device_scalars = True
+        return m, SearchStep(m, arch, torch.optim.Adam(m.parameters(), lr=0.0, capturable=True))
+    batches = [(P.vqa_batch(31, DEV), P.vqa_batch(32, DEV)), (P.vqa_batch(41, DEV), P.vqa_batch(42, DEV))]
+    m1, eager = make()
+    m2, st = make()
+    graphed = GraphedSearchStep(st, *batches[0], 1e-3, unrolled=unrolled, warmup=2)
+    for _ in range(2):
+        eager.step(*batches[0], 1e-3, unrolled=unrolled)
+    return m1, eager, m2, graphed, batches
+
+
+def test_graphed_search_step_matches_eager():
+    """CUDA-graph replay of the whole search step == the eager step (first-order alpha-step + w-step).
+    Learning rates are 0, so both models hold bit-identical weights and must agree on the loss, the
+    alpha/beta grads and every weight grad; the second batch exercises the copy into the static inputs."""
+    from helpers import assert_close
+    m1, eager, m2, graphed, batches = _graph_pair(unrolled=False)
+    for train, valid in batches:
+        loss_e = eager.step(train, valid, 1e-3, unrolled=False)
+        loss_g = graphed(train, valid)
+        torch.cuda.synchronize()
+        assert_close(loss_g, loss_e, 1e-6, "loss")
+        for x, y in zip(m2.arch_parameters(), m1.arch_parameters()):
+            assert_close(x.grad, y.grad, 1e-5, "arch grad")
+        for (k, x), y in zip(m2.named_parameters(), m1.parameters()):
+            assert_close(x.grad, y.grad, 1e-4, k)
+    k = "img_encoder.darts.stem.1.num_batches_tracked"       # BN side effects advance identically
+    assert int(m2.state_dict()[k]) == int(m1.state_dict()[k])
+
+
+def test_graphed_unrolled_step_runs():
+    """The unrolled (HVP) step also captures and replays.  Its w +- R v updates leave one-ulp residue in the
+    weights that depends on fp32 atomic ordering, and with 2-sample tensors a single ReLU input within 1e-6 of
+    zero then moves a gradient by ~1e-3, so only the loss and the alpha/beta grads are
+    compared, loosely."""
+    from helpers import assert_close
+    m1, eager, m2, graphed, batches = _graph_pair(unrolled=True)
+    for train, valid in batches:
+        loss_e = eager.step(train, valid, 1e-3, unrolled=True)
+        loss_g = graphed(train, valid)
+        torch.cuda.synchronize()
+        assert_close(loss_g, loss_e, 1e-4, "loss")
+        for x, y in zip(m2.arch_parameters(), m1.arch_parameters()):
+            assert_close(x.grad, y.grad, 5e-3, "arch grad")
+
+
 def test_native_library_is_the_one_running():
     import pcd_native
     lib = pcd_native.load_cuda()
