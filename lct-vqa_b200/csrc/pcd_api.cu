@@ -39,17 +39,17 @@ static int zero_async(void* p, size_t bytes, void* stream) {
 }
 
 // ---- kernel body adaptors -----------------------------------------------------------------------------
-template <int C> struct KCombine { static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
-struct KNorm { static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
-struct KStem { static const char* name() { return "Stem"; } static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
-struct KGapF { static const char* name() { return "GapF"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };
-struct KGapB { static const char* name() { return "GapB"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_bwd_body(a, x); } };
-struct KShuffle { static const char* name() { return "Shuffle"; } static PCD_D void run(const ShuffleArgs& a, int x, int y, int z, float*) { shuffle_body(a, x, y, z); } };
-template <int C> struct KNodeStats { static const char* name() { return C == 4 ? "node_stats_c4" : C == 8 ? "node_stats_c8" : "node_stats_c16"; } static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
-struct KSourceGrad { static const char* name() { return "SourceGrad"; } static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
-struct KArchGrads { static const char* name() { return "ArchGrads"; } static PCD_D void run(const ArchGradArgs& a, int, int, int, float*) { arch_grads_body(a); } };
-struct KBnBwdStats { static const char* name() { return "BnBwdStats"; } static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
-struct KStemBwd { static const char* name() { return "StemBwd"; } static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd_body(a, x, a.nblocks_launch, sm); } };
+template <int C> struct KCombine { static constexpr int kMinBlocks = 1; static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
+struct KNorm { static constexpr int kMinBlocks = 1; static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
+struct KStem { static constexpr int kMinBlocks = 1; static const char* name() { return "Stem"; } static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
+struct KGapF { static constexpr int kMinBlocks = 1; static const char* name() { return "GapF"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };
+struct KGapB { static constexpr int kMinBlocks = 1; static const char* name() { return "GapB"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_bwd_body(a, x); } };
+struct KShuffle { static constexpr int kMinBlocks = 1; static const char* name() { return "Shuffle"; } static PCD_D void run(const ShuffleArgs& a, int x, int y, int z, float*) { shuffle_body(a, x, y, z); } };
+template <int C> struct KNodeStats { static constexpr int kMinBlocks = 1; static const char* name() { return C == 4 ? "node_stats_c4" : C == 8 ? "node_stats_c8" : "node_stats_c16"; } static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
+struct KSourceGrad { static constexpr int kMinBlocks = 1; static const char* name() { return "SourceGrad"; } static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
+struct KArchGrads { static constexpr int kMinBlocks = 1; static const char* name() { return "ArchGrads"; } static PCD_D void run(const ArchGradArgs& a, int, int, int, float* sm) { arch_grads_body(a, sm); } };
+struct KBnBwdStats { static constexpr int kMinBlocks = 1; static const char* name() { return "BnBwdStats"; } static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
+struct KStemBwd { static constexpr int kMinBlocks = 1; static const char* name() { return "StemBwd"; } static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd_body(a, x, a.nblocks_launch, sm); } };
 
 #define PCD_DISPATCH_C(c, EXPR)                         \
     do {                                                \
@@ -470,7 +470,7 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
         ag.e[e].gw = a->grad_weights + e * PCD_NUM_PRIMITIVES;
         ag.e[e].gw2 = a->grad_weights2 + e;
     }
-    PCD_TRY((launch<KArchGrads, ArchGradArgs>(ag, 1, 1, 1, 0, stream)));
+    PCD_TRY((launch<KArchGrads, ArchGradArgs>(ag, 1, 1, 1, arch_grads_smem_floats(), stream)));
     // 5. preprocess backward
     PCD_TRY(run_pre_backward(L.B, L.Cpp, L.C, L.H0, L.W0, L.redp, eps, a->s0, a->params + L.pre_par[0],
                              a->saved + L.pre_out[0], a->work + L.pre_dout[0], a->stats + L.pre_stats[0],
@@ -559,7 +559,7 @@ int pcd_mixedop_backward(const pcd_mixedop_bwd_args* a, void* stream) {
     ag.c = q.c; ag.nedges = 1; ag.eps = a->shape.bn_eps;
     ag.e[0].stats = a->stats; ag.e[0].bstats = a->bstats; ag.e[0].alpha = a->weights; ag.e[0].beta = nullptr;
     ag.e[0].stride = q.S; ag.e[0].count = (double)q.B * q.Ho * q.Wo; ag.e[0].gw = a->grad_weights; ag.e[0].gw2 = nullptr;
-    return launch<KArchGrads, ArchGradArgs>(ag, 1, 1, 1, 0, stream);
+    return launch<KArchGrads, ArchGradArgs>(ag, 1, 1, 1, arch_grads_smem_floats(), stream);
 }
 
 // ---- stem ---------------------------------------------------------------------------------------------------

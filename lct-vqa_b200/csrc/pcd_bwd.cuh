@@ -302,35 +302,41 @@ struct ArchGradArgs {
     ArchEdge e[PCD_MAX_EDGES_CONST];
 };
 
-PCD_HD void arch_grads_body(const ArchGradArgs& a) {
-    PCD_FOR(ei, a.nedges) {
+PCD_HOSTDEV size_t arch_grads_smem_floats() { return 2 * PCD_MAX_EDGES_CONST * 8 + 16; }
+
+PCD_HD void arch_grads_body(const ArchGradArgs& a, float* smem) {
+    double* D = reinterpret_cast<double*>(smem);          // [edge][8]
+    PCD_FOR(t, a.nedges * 8) {
+        const int ei = t >> 3, k = t & 7;
         const ArchEdge& e = a.e[ei];
         const int c = a.c, s = e.stride;
-        const float beta = e.beta ? e.beta[0] : 1.f;
-        const int bns[7] = {bn_p1(), bn_p2(), bn_unit(s, 1), bn_unit(s, 3), bn_unit(s, 4), bn_unit(s, 5), bn_f()};
-        const int prim[7] = {1, 2, 4, 5, 6, 7, 3};
-        double D[8];
-        for (int k = 0; k < 8; ++k) D[k] = 0.0;
-        for (int k = 0; k < 7; ++k) {
-            if (k == 6 && s != 2) break;
-            double acc = 0.0;
+        // primitive k -> BN id (or -1): none | max | avg | skip | sep3 | sep5 | dil3 | dil5
+        int bn = -1;
+        if (k == 1) bn = bn_p1();
+        else if (k == 2) bn = bn_p2();
+        else if (k == 3) bn = (s == 2) ? bn_f() : -1;
+        else if (k >= 4) bn = bn_unit(s, k == 4 ? 1 : k == 5 ? 3 : k == 6 ? 4 : 5);
+        double acc = 0.0;
+        if (bn >= 0) {
             for (int j = 0; j < c; ++j) {
-                BnC b = bn_consts(e.stats, c, bns[k], j, e.count, a.eps);
-                acc += (double)b.rstd * (e.bstats[bs_sz(bns[k]) * c + j] - (double)b.mean * e.bstats[bs_s0() * c + j]);
+                BnC b = bn_consts(e.stats, c, bn, j, e.count, a.eps);
+                acc += (double)b.rstd * (e.bstats[bs_sz(bn) * c + j] - (double)b.mean * e.bstats[bs_s0() * c + j]);
             }
-            D[prim[k]] = acc;
-        }
-        if (s == 1) {
-            double acc = 0.0;
+        } else if (k == 3) {
             for (int j = 0; j < c; ++j) acc += e.bstats[bs_sx() * c + j];
-            D[3] = acc;
         }
-        double db = e.bstats[15 * c];
-        for (int k = 0; k < 8; ++k) {
-            e.gw[k] = (float)(beta * D[k]);
-            db += (double)e.alpha[k] * D[k];
+        D[t] = acc;
+        const float beta = e.beta ? e.beta[0] : 1.f;
+        e.gw[k] = (float)(beta * acc);
+    }
+    PCD_SYNC();
+    PCD_FOR(ei, a.nedges) {
+        const ArchEdge& e = a.e[ei];
+        if (e.gw2) {
+            double db = e.bstats[15 * a.c];
+            for (int k = 0; k < 8; ++k) db += (double)e.alpha[k] * D[ei * 8 + k];
+            e.gw2[0] = (float)db;
         }
-        if (e.gw2) e.gw2[0] = (float)db;
     }
 }
 

@@ -440,11 +440,19 @@ PCD_HD void dz_dt_tile(float* DT, float* DZ, int RH, int IW, int halo_y, const f
 }
 
 // dWpw[co][ci] += sum_p DZ[co][p] * t[ci][p] over the tile.  (C/4)^2 output groups x NSL pixel slices.
+template <int C>
+struct WgradPw {
+    static constexpr int NOG = (C / 4) * (C / 4);
+    static constexpr int NT = (C == 16) ? 128 : 256;      // tasks (C == 16: fewer, to keep P small)
+    static constexpr int NSL = NT / NOG;
+    static constexpr int PFLOATS = 16 * NT;
+};
+
 template <int C, bool FAST>
 PCD_HD void wgrad_pw(const float* DZ, const float* t_slot, float* gw, float* P, float* P2, const Geo& g) {
-    constexpr int NOG = (C / 4) * (C / 4), NSL = 256 / NOG;
+    constexpr int NOG = WgradPw<C>::NOG, NSL = WgradPw<C>::NSL, NT = WgradPw<C>::NT;
     const int NPIX = g.TH * g.TW, SPS = (NPIX / 4 + NSL - 1) / NSL, PW4 = g.TW / 4;   // strips per slice
-    PCD_FOR(task, 256) {
+    PCD_FOR(task, NT) {
         const int og = task / NSL, sl = task - og * NSL;
         const int co0 = (og / (C / 4)) * 4, ci0 = (og % (C / 4)) * 4;
         float acc[4][4];
@@ -473,9 +481,9 @@ PCD_HD void wgrad_pw(const float* DZ, const float* t_slot, float* gw, float* P, 
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) P[(i * 4 + k) * 256 + task] = acc[i][k];
+            for (int k = 0; k < 4; ++k) P[(i * 4 + k) * NT + task] = acc[i][k];
     }
-    reduce_columns<8>(P, P2, 16, NOG, NSL, 256, [&](int og, int k, float v) {
+    reduce_columns<4>(P, P2, 16, NOG, NSL, NT, [&](int og, int k, float v) {
         const int co = (og / (C / 4)) * 4 + (k >> 2), ci = (og % (C / 4)) * 4 + (k & 3);
         pcd_atomic_add(gw + co * C + ci, v);
     });
@@ -502,15 +510,19 @@ PCD_HD void wgrad_dw(const float* DT, int RH, int IW, int halo_y, const float* I
 #pragma unroll
         for (int k = 0; k < KS * KS; ++k) P[k * NT + task] = acc[k];
     }
-    reduce_columns<8>(P, P2, KS * KS, C, NPATCH, NT, [&](int ch, int k, float v) {
+    reduce_columns<4>(P, P2, KS * KS, C, NPATCH, NT, [&](int ch, int k, float v) {
         pcd_atomic_add(gw + ch * KS * KS + k, v);
     });
 }
 
+constexpr int kWgradNP = 4;     // partials per (value, group) in the weight-grad column reductions
+
+PCD_HOSTDEV size_t wgrad_p2_floats(int C) { return (size_t)25 * C * kWgradNP + 64; }
+
 PCD_HOSTDEV size_t wgrad_scratch_floats(int C, int TH, int TW) {
-    // DZ [C][NPIX] + P for wgrad_pw (16*256); wgrad_dw's P (25*C*NPATCH) aliases the same region
-    size_t a = (size_t)C * TH * TW + 16 * 256, b = (size_t)25 * C * (TH / 4) * (TW / 4);
-    return (a > b ? a : b) + 25 * C * 8 + 64;
+    // DZ [C][NPIX] + P for wgrad_pw (16 * tasks); wgrad_dw's P (25*C*NPATCH) aliases the same region; then P2
+    size_t a = (size_t)C * TH * TW + 16 * (C == 16 ? 128 : 256), b = (size_t)25 * C * (TH / 4) * (TW / 4);
+    return (a > b ? a : b) + wgrad_p2_floats(C);
 }
 
 // ---- stage B ------------------------------------------------------------------------------------------------
@@ -537,7 +549,7 @@ PCD_HD void bwdB_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, int hal
     float* DZ = a.need_wgrad ? SCR : nullptr;
     float* Ppw = SCR + C * NPIX;
     float* Pdw = SCR;
-    float* P2 = a.need_wgrad ? SCR + (wgrad_scratch_floats(C, TH, TW) - 25 * C * 8 - 64) : SCR + 2 * C * NPATCH;
+    float* P2 = a.need_wgrad ? SCR + (wgrad_scratch_floats(C, TH, TW) - wgrad_p2_floats(C)) : SCR + 2 * C * NPATCH;
     const int uA = half ? 2 : 0, uB = uA + 1;
     const long long nslot = (long long)a.B * C * a.Ho * a.Wo, HW = (long long)a.Ho * a.Wo;
     const double cnt = (double)a.B * a.Ho * a.Wo;
@@ -681,7 +693,7 @@ PCD_HD void bwdA_conv_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, in
     float* DZ = a.need_wgrad ? SCR : nullptr;
     float* Ppw = SCR + C * NPIX;
     float* Pdw = SCR;
-    float* P2 = SCR + (wgrad_scratch_floats(C, TH, TW) - 25 * C * 8 - 64);
+    float* P2 = SCR + (wgrad_scratch_floats(C, TH, TW) - wgrad_p2_floats(C));
     const long long nslot = (long long)a.B * C * a.Ho * a.Wo, HW = (long long)a.Ho * a.Wo;
     const double cnt = (double)a.B * a.Ho * a.Wo;
     const float beta = e.beta ? e.beta[0] : 1.f;
@@ -945,7 +957,7 @@ PCD_HD void bwdA_fr_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, floa
 #pragma unroll
                 for (int k = 0; k < 4; ++k) P[(i * 4 + k) * 256 + task] = acc[i][k];
         }
-        reduce_columns<8>(P, P2, 16, NOG, NSL, 256, [&](int og, int k, float v) {
+        reduce_columns<4>(P, P2, 16, NOG, NSL, 256, [&](int og, int k, float v) {
             const int co = (og / (C / 4)) * 4 + (k >> 2), ci = (og % (C / 4)) * 4 + (k & 3);
             pcd_atomic_add(e.gpar + co * C + ci, v);
         });

@@ -343,10 +343,11 @@ PCD_HD void gap_bwd_body(const GapArgs& a /* x = gy (OHxOW), y = gx (HxW) */, in
             const int x = (int)(i % a.W), y = (int)((i / a.W) % a.H);
             const long long nc = i / (a.W * a.H);
             float s = 0.f;
-            for (int oy = 0; oy < a.OH; ++oy) {
+            const int oyc = (y * a.OH) / a.H, oxc = (x * a.OW) / a.W;     // windows overlap by at most one neighbour
+            for (int oy = (oyc > 0 ? oyc - 1 : 0); oy <= oyc + 1 && oy < a.OH; ++oy) {
                 const int y0 = (oy * a.H) / a.OH, y1 = ((oy + 1) * a.H + a.OH - 1) / a.OH;
                 if (y < y0 || y >= y1) continue;
-                for (int ox = 0; ox < a.OW; ++ox) {
+                for (int ox = (oxc > 0 ? oxc - 1 : 0); ox <= oxc + 1 && ox < a.OW; ++ox) {
                     const int x0 = (ox * a.W) / a.OW, x1 = ((ox + 1) * a.W + a.OW - 1) / a.OW;
                     if (x < x0 || x >= x1) continue;
                     s += a.x[(nc * a.OH + oy) * a.OW + ox] / (float)((y1 - y0) * (x1 - x0));

@@ -5,7 +5,7 @@
 namespace pcd {
 
 template <int C, int S, int TH, int TW> struct KBwdA {
-    static const char* name() {
+    static constexpr int kMinBlocks = 2; static const char* name() {
         return S == 1 ? (C == 4 ? "bwdA_c4_s1" : C == 8 ? "bwdA_c8_s1" : "bwdA_c16_s1")
                       : (C == 4 ? "bwdA_c4_s2" : C == 8 ? "bwdA_c8_s2" : "bwdA_c16_s2");
     }

@@ -5,7 +5,7 @@
 namespace pcd {
 
 template <int C, int TH, int TW> struct KBwdB {
-    static const char* name() { return C == 4 ? "bwdB_c4" : C == 8 ? "bwdB_c8" : "bwdB_c16"; }
+    static constexpr int kMinBlocks = 2; static const char* name() { return C == 4 ? "bwdB_c4" : C == 8 ? "bwdB_c8" : "bwdB_c16"; }
     static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdB_body<C, TH, TW>(a, x, y, z, sm); }
 };
 

@@ -5,14 +5,14 @@
 namespace pcd {
 
 template <int C, int S, int TH, int TW> struct KFwdA {
-    static const char* name() {
+    static constexpr int kMinBlocks = 3; static const char* name() {
         return S == 1 ? (C == 4 ? "fwdA_c4_s1" : C == 8 ? "fwdA_c8_s1" : "fwdA_c16_s1")
                       : (C == 4 ? "fwdA_c4_s2" : C == 8 ? "fwdA_c8_s2" : "fwdA_c16_s2");
     }
     static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { fwdA_body<C, S, TH, TW>(a, x, y, z, sm); }
 };
 template <int C, int TH, int TW> struct KFwdB {
-    static const char* name() { return C == 4 ? "fwdB_c4" : C == 8 ? "fwdB_c8" : "fwdB_c16"; }
+    static constexpr int kMinBlocks = 3; static const char* name() { return C == 4 ? "fwdB_c4" : C == 8 ? "fwdB_c8" : "fwdB_c16"; }
     static PCD_D void run(const PassArgs& a, int x, int y, int z, float* sm) { fwdB_body<C, TH, TW>(a, x, y, z, sm); }
 };
 

@@ -6,11 +6,11 @@
 namespace pcd {
 
 template <int COUT> struct KPreConv {
-    static const char* name() { return COUT == 16 ? "pre_conv_16" : COUT == 32 ? "pre_conv_32" : "pre_conv_64"; }
+    static constexpr int kMinBlocks = 1; static const char* name() { return COUT == 16 ? "pre_conv_16" : COUT == 32 ? "pre_conv_32" : "pre_conv_64"; }
     static PCD_D void run(const PreArgs& a, int x, int y, int, float* sm) { pre_conv_body<COUT>(a, x, y, sm); }
 };
 template <int COUT> struct KPreBwd {
-    static const char* name() { return COUT == 16 ? "pre_bwd_16" : COUT == 32 ? "pre_bwd_32" : "pre_bwd_64"; }
+    static constexpr int kMinBlocks = 1; static const char* name() { return COUT == 16 ? "pre_bwd_16" : COUT == 32 ? "pre_bwd_32" : "pre_bwd_64"; }
     static PCD_D void run(const PreBwdArgs& a, int x, int y, int, float* sm) { pre_bwd_body<COUT>(a, x, y, sm); }
 };
 

@@ -30,7 +30,7 @@ int register_kernel(const char* name);
 #define PCD_D __device__ __forceinline__
 
 template <class Body, class Args>
-__global__ void __launch_bounds__(kThreads) pcd_kernel(const Args a) {
+__global__ void __launch_bounds__(kThreads, Body::kMinBlocks) pcd_kernel(const Args a) {
     extern __shared__ F4 pcd_smem4[];
     Body::run(a, blockIdx.x, blockIdx.y, blockIdx.z, reinterpret_cast<float*>(pcd_smem4));
 }
