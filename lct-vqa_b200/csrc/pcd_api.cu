@@ -176,6 +176,7 @@ static int run_pre_backward(int B, int Cin, int Cout, int Hin, int Win, int fr, 
     memset(&a, 0, sizeof a);
     a.B = B; a.Cin = Cin; a.Cout = Cout; a.Hin = Hin; a.Win = Win; a.Ho = Ho; a.Wo = Wo; a.fr = fr;
     a.x = x; a.w = w; a.y = y; a.dy = dy; a.stats = stats; a.bstats = bstats; a.eps = eps; a.dx = dx; a.gw = gw;
+    a.chunks_per_block = 0;      // chosen by the launcher
     return launch_pre_bwd(a, stream);
 }
 

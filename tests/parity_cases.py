@@ -150,6 +150,37 @@ def mixed_vs_oracle(C, stride, B, H, device, seed=7, check_grads=True):
             assert_close(v, buf[k], 1e-5, k)
 
 
+def pre_vs_oracle(c_in, c_out, fr, B, H, device, seed=11):
+    """Stand-alone preprocess op (ReLUConvBN 1x1 / FactorizedReduce, affine=False) vs the oracle on CPU."""
+    import config
+    config.DEVICE = device
+    from pcdarts.operations import FactorizedReduce, ReLUConvBN
+    m = (FactorizedReduce(c_in, c_out, affine=False) if fr else ReLUConvBN(c_in, c_out, 1, 1, 0, affine=False)).train()
+    _fill(m, seed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    par, buf = O.split_state(sd)
+    for v in par.values():
+        v.requires_grad_(True)
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, c_in, H, H, generator=gen)
+    Ho = H // 2 if fr else H
+    G = torch.randn(B, c_out, Ho, Ho, generator=gen)
+    xr = x.clone().requires_grad_(True)
+    yr = (O.factorized_reduce if fr else O.relu_conv_bn)(par, O.BNState(buf), "", xr)
+    (yr * G).sum().backward()
+    m.to(device)
+    xd = x.to(device).requires_grad_(True)
+    y = m(xd)
+    assert_close(y, yr, REL_TOL, "y")
+    (y * G.to(device)).sum().backward()
+    assert_close(xd.grad, xr.grad, REL_TOL, "dx")
+    for k, p_ in m.named_parameters():
+        assert_close(p_.grad, par[k].grad, REL_TOL, k)
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            assert_close(v, buf[k], 1e-5, k)
+
+
 # ---- whole VQA model, architect, w-step (goldens: tests/golden/make_golden.py) ------------------------
 VQA_DIMS = dict(embed_size=16, qst_vocab_size=40, ans_vocab_size=12, word_embed_size=10, num_layers=1,
                 hidden_size=16)

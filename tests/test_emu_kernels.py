@@ -33,6 +33,14 @@ def test_mixed_op_fixed_tiles_emulated(C, stride, B, H):
     P.mixed_vs_oracle(C, stride, B, H, "cpu")
 
 
+# preprocess 1x1 GEMM kernels: ragged pixel tiles, FactorizedReduce (fast and generic loads), partial channel chunks
+@pytest.mark.parametrize("c_in,c_out,fr,B,H", [(48, 16, False, 2, 16), (48, 32, False, 1, 20), (64, 64, True, 2, 16),
+                                                 (128, 64, False, 1, 18), (64, 32, True, 1, 12), (40, 16, False, 1, 9),
+                                                 (256, 64, False, 1, 16)])
+def test_preprocess_emulated(c_in, c_out, fr, B, H):
+    P.pre_vs_oracle(c_in, c_out, fr, B, H, "cpu")
+
+
 def test_network_emulated():
     P.network_case("cpu")
 

@@ -33,6 +33,16 @@ def test_mixed_op_production_shapes_vs_oracle(C, stride, B, H):
     P.mixed_vs_oracle(C, stride, B, H, DEV)
 
 
+# the eight production preprocess shapes at reduced batch, plus shapes that make one block loop over
+# several input-channel chunks (many pixel tiles) and shapes that split the chunks over blockIdx.z (few tiles)
+@pytest.mark.parametrize("c_in,c_out,fr,B,H", [
+    (48, 16, False, 4, 64), (48, 32, False, 4, 64), (64, 32, False, 4, 64), (64, 64, True, 4, 64),
+    (128, 64, False, 4, 32), (128, 64, True, 4, 32), (256, 64, False, 4, 16), (256, 64, False, 40, 64),
+    (128, 64, True, 40, 64), (64, 32, True, 2, 8), (48, 16, False, 1, 9)])
+def test_preprocess_vs_oracle(c_in, c_out, fr, B, H):
+    P.pre_vs_oracle(c_in, c_out, fr, B, H, DEV)
+
+
 def test_vqa_model_golden():
     P.vqa_case(DEV)
 
