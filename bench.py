@@ -36,7 +36,7 @@ UNIT = "steps/s"
 DIMS = dict(embed_size=512, ans_vocab_size=1000, word_embed_size=300, num_layers=1, hidden_size=512)
 # algorithmic bytes of all 56 MixedOp edges at B=64 (fwd 1241.5 MB, fwd+bwd 2977.5 MB)
 MIXED_FWD_MB_B64, MIXED_BWD_MB_B64 = 1241.5136, 1736.0
-MIXED_KERNELS = ("fwdA", "fwdB", "combine", "node_stats", "bwdB", "bwdA", "SourceGrad", "ArchGrads")
+MIXED_KERNELS = ("fwdA", "fwdB", "combine", "node_stats", "bwdB", "bwdA", "wgrad", "SourceGrad", "ArchGrads")
 EDGE_SHAPES = [("T1 C16@64 s1", 16, 1, 64, 14), ("T2 C32 64->32 s2", 32, 2, 64, 8), ("T3 C32@32 s1", 32, 1, 32, 6),
                ("T4 C64 32->16 s2", 64, 2, 32, 8), ("T5 C64@16 s1", 64, 1, 16, 20)]
 
@@ -306,7 +306,7 @@ def run_b200(a):
         alg_mb = (n_fwd * MIXED_FWD_MB_B64 + n_bwd * MIXED_BWD_MB_B64) * a.batch / 64.0
         achieved = alg_mb / 1e3 / (mixed_ms / 1e3)
         top = next(iter(by_kernel))
-        roofline = {"bound": "hbm", "kernel": "MixedOp kernel group (fwdA,fwdB,combine | node_stats,bwdB,bwdA,"
+        roofline = {"bound": "hbm", "kernel": "MixedOp kernel group (fwdA,fwdB,combine | node_stats,bwdB,bwdA,wgrad,"
                                               "source_grad,arch_grads): all 56 edges x all passes of one step",
                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                     "algorithmic_mb_per_step": alg_mb, "kernel_ms_per_step": mixed_ms, "peak_source": peak_src,

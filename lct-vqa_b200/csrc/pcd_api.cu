@@ -117,18 +117,56 @@ static int run_node_stats(int B, int c, int Ho, int Wo, const float* dn, long lo
     return PCD_OK;
 }
 
-static int run_edge_bwd(const EdgeGeom& q, const EdgeG* edges, int n, float eps, int need_wgrad, void* stream) {
-    if (n == 0) return PCD_OK;
-    if (n > kMaxEdgesPerLaunch) return PCD_ERR_ARG;
-    EdgeBwdArgs a;
+static void fill_edge_bwd_args(EdgeBwdArgs& a, const EdgeGeom& q, const EdgeG* edges, int n, float eps, int need_wgrad, bool* al) {
     memset(&a, 0, sizeof a);
     a.B = q.B; a.Hs = q.Hs; a.Ws = q.Ws; a.Ho = q.Ho; a.Wo = q.Wo; a.S = q.S; a.eps = eps; a.nedges = n;
     a.need_wgrad = need_wgrad;
-    bool al = true;
+    *al = true;
     for (int i = 0; i < n; ++i) {
         a.e[i] = edges[i];
-        al = al && aligned16(edges[i].x) && aligned16(edges[i].saved) && aligned16(edges[i].dn) && aligned16(edges[i].ga) &&
-             aligned16(edges[i].pd) && edges[i].x_ns % 4 == 0 && edges[i].dn_ns % 4 == 0;
+        *al = *al && aligned16(edges[i].x) && aligned16(edges[i].saved) && aligned16(edges[i].dn) && aligned16(edges[i].ga) &&
+              aligned16(edges[i].pd) && edges[i].x_ns % 4 == 0 && edges[i].dn_ns % 4 == 0;
+    }
+}
+
+// v3 weight-gradient jobs for edges whose data jobs already ran (any number of edges, one stride)
+static int run_edge_wgrad2(const EdgeGeom& q, const EdgeG* edges, int n, float eps, void* stream) {
+    int thA = 0;
+    if (!bwd2_tile(q.c, q.S, q.Ho, q.Wo, &thA)) return PCD_ERR_UNSUPPORTED;
+    for (int i0 = 0; i0 < n; i0 += kMaxEdgesPerLaunch) {
+        const int m = (n - i0 < kMaxEdgesPerLaunch) ? n - i0 : kMaxEdgesPerLaunch;
+        EdgeBwdArgs a;
+        bool al;
+        fill_edge_bwd_args(a, q, edges + i0, m, eps, 1, &al);
+        a.TH = thA; a.TW = q.Wo; a.tiles_x = 1;
+        PCD_TRY(launch_wgrad2(a, q.c, m * bwdA_njobs(q.S), stream));
+    }
+    return PCD_OK;
+}
+
+// Backward of a group of edges with one geometry.  Production geometries run the v3 data kernels; their weight
+// gradients are either launched here (defer == nullptr) or left to the caller (*defer set to 1), which batches
+// them over the whole cell.  Other geometries run the generic v2 kernels (weight grads inline).
+static int run_edge_bwd(const EdgeGeom& q, const EdgeG* edges, int n, float eps, int need_wgrad, void* stream,
+                        int* defer = nullptr) {
+    if (defer) *defer = 0;
+    if (n == 0) return PCD_OK;
+    if (n > kMaxEdgesPerLaunch) return PCD_ERR_ARG;
+    EdgeBwdArgs a;
+    bool al;
+    fill_edge_bwd_args(a, q, edges, n, eps, need_wgrad, &al);
+    int thA = 0, thB = 0;
+    if (al && q.Ws % 4 == 0 && bwd2_tile(q.c, q.S, q.Ho, q.Wo, &thA) && bwd2_tile(q.c, 1, q.Ho, q.Wo, &thB)) {
+        a.need_wgrad = 0;
+        a.TH = thB; a.TW = q.Wo; a.tiles_x = 1;
+        PCD_TRY(launch_bwdB2(a, q.c, n * 2, stream));
+        a.TH = thA;
+        PCD_TRY(launch_bwdA2(a, q.c, n * bwdA_njobs(q.S), stream));
+        if (need_wgrad) {
+            if (defer) *defer = 1;
+            else PCD_TRY(run_edge_wgrad2(q, edges, n, eps, stream));
+        }
+        return PCD_OK;
     }
     Tile tb = pick_tile(q.Ho, q.Wo, q.c, 4096);
     a.TH = tb.TH; a.TW = tb.TW; a.tiles_x = tb.tiles_x;
@@ -391,6 +429,9 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
         ns = node / L.B;
         return a->work + L.dn[i];
     };
+    EdgeG wq[2][PCD_MAX_EDGES];          // edges whose weight-grad jobs are deferred, by stride
+    EdgeGeom wgeo[2];
+    int nwq[2] = {0, 0};
     for (int i = 3; i >= 0; --i) {
         long long dn_ns;
         const float* dn = dn_ptr(i, dn_ns);
@@ -429,7 +470,13 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
             q.S = L.stride[e]; q.Hs = s.H; q.Ws = s.W;
             ++n;
         }
-        PCD_TRY(run_edge_bwd(q, eg, n, eps, a->need_param_grads, stream));
+        int deferred = 0;
+        PCD_TRY(run_edge_bwd(q, eg, n, eps, a->need_param_grads, stream, &deferred));
+        if (deferred && n > 0) {
+            const int g = q.S - 1;
+            wgeo[g] = q;
+            for (int k = 0; k < n; ++k) wq[g][nwq[g]++] = eg[k];
+        }
         // 3. gradient of the source state(s)
         for (int j = (i == 0 ? 0 : i + 1); j <= (i == 0 ? 1 : i + 1); ++j) {
             StateRef s = state_ref(L, a->saved, a->out, j);
@@ -457,6 +504,8 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
             PCD_TRY(run_source_grad(sg, stream));
         }
     }
+    for (int g = 0; g < 2; ++g)
+        if (nwq[g]) PCD_TRY(run_edge_wgrad2(wgeo[g], wq[g], nwq[g], eps, stream));
     // 4. d softmax(alpha) rows, d beta
     ArchGradArgs ag;
     memset(&ag, 0, sizeof ag);

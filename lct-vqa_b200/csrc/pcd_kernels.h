@@ -10,6 +10,11 @@ int launch_fwdA(const PassArgs& a, int c, bool fast, int gx, int gy, int gz, voi
 int launch_fwdB(const PassArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
 int launch_bwdA(const EdgeBwdArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
 int launch_bwdB(const EdgeBwdArgs& a, int c, bool fast, int gx, int gy, int gz, void* stream);
+// v3 backward (pcd_edge_bwd2.cuh): production geometries only; a.TH / a.TW hold the tile (TW == Wo)
+bool bwd2_tile(int c, int S, int Ho, int Wo, int* TH);
+int launch_bwdB2(const EdgeBwdArgs& a, int c, int gz, void* stream);
+int launch_bwdA2(const EdgeBwdArgs& a, int c, int gz, void* stream);
+int launch_wgrad2(const EdgeBwdArgs& a, int c, int gz, void* stream);
 struct PreArgs;
 struct PreBwdArgs;
 int launch_pre_conv(const PreArgs& a, void* stream);

@@ -181,6 +181,43 @@ def pre_vs_oracle(c_in, c_out, fr, B, H, device, seed=11):
             assert_close(v, buf[k], 1e-5, k)
 
 
+def cell_vs_oracle(cpp, cp, C, red, rp, B, H, device, seed=13, act_only=False):
+    """A whole Cell at a production spatial size (compile-time-tile kernels, deferred weight-grad launch) vs the oracle."""
+    import config
+    config.DEVICE = device
+    from pcdarts.model_search import Cell
+    m = Cell(4, 4, cpp, cp, C, red, rp).train()
+    _fill(m, seed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    par, buf = O.split_state(sd)
+    for v in par.values():
+        v.requires_grad_(not act_only)
+    gen = torch.Generator().manual_seed(seed)
+    H0 = 2 * H if rp else H
+    Ho = H // 2 if red else H
+    s0 = torch.randn(B, cpp, H0, H0, generator=gen)
+    s1 = torch.randn(B, cp, H, H, generator=gen)
+    w = torch.softmax(torch.randn(14, 8, generator=gen), -1)
+    w2 = torch.softmax(torch.randn(14, generator=gen), 0)
+    G = torch.randn(B, 4 * C, Ho, Ho, generator=gen)
+    ref_in = [t.clone().requires_grad_(True) for t in (s0, s1, w, w2)]
+    yr = O.cell_forward(par, O.BNState(buf), "", *ref_in, red, rp)
+    (yr * G).sum().backward()
+    m.to(device)
+    if act_only:
+        for p_ in m.parameters():
+            p_.requires_grad_(False)
+    ins = [t.to(device).requires_grad_(True) for t in (s0, s1, w, w2)]
+    y = m(*ins)
+    assert_close(y, yr, REL_TOL, "y")
+    (y * G.to(device)).sum().backward()
+    for t, r, k in zip(ins, ref_in, ("ds0", "ds1", "dw", "dw2")):
+        assert_close(t.grad, r.grad, REL_TOL, k)
+    if not act_only:
+        for k, p_ in m.named_parameters():
+            assert_close(p_.grad, par[k].grad, REL_TOL, k)
+
+
 # ---- whole VQA model, architect, w-step (goldens: tests/golden/make_golden.py) ------------------------
 VQA_DIMS = dict(embed_size=16, qst_vocab_size=40, ans_vocab_size=12, word_embed_size=10, num_layers=1,
                 hidden_size=16)

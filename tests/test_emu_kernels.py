@@ -41,6 +41,12 @@ def test_preprocess_emulated(c_in, c_out, fr, B, H):
     P.pre_vs_oracle(c_in, c_out, fr, B, H, "cpu")
 
 
+# a production-geometry cell (v3 backward kernels + deferred weight-grad launch), one image
+@pytest.mark.parametrize("cpp,cp,C,red,rp,H", [(128, 256, 64, False, True, 16), (64, 128, 64, True, True, 32)])
+def test_cell_production_geometry_emulated(cpp, cp, C, red, rp, H):
+    P.cell_vs_oracle(cpp, cp, C, red, rp, 1, H, "cpu")
+
+
 def test_network_emulated():
     P.network_case("cpu")
 

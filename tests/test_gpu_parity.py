@@ -43,6 +43,15 @@ def test_preprocess_vs_oracle(c_in, c_out, fr, B, H):
     P.pre_vs_oracle(c_in, c_out, fr, B, H, DEV)
 
 
+# the four production cells (C=16@64, reduce C=32 64->32, reduce C=64 32->16, C=64@16) at batch 2: v3 backward kernels
+# with the cell-wide deferred weight-gradient launch; once more with frozen weights (activation-only backward, HVP passes)
+@pytest.mark.parametrize("cpp,cp,C,red,rp,H", [(48, 48, 16, False, False, 64), (48, 64, 32, True, False, 64),
+                                               (64, 128, 64, True, True, 32), (128, 256, 64, False, True, 16)])
+@pytest.mark.parametrize("act_only", [False, True])
+def test_cell_production_geometry_vs_oracle(cpp, cp, C, red, rp, H, act_only):
+    P.cell_vs_oracle(cpp, cp, C, red, rp, 2, H, DEV, act_only=act_only)
+
+
 def test_vqa_model_golden():
     P.vqa_case(DEV)
 
