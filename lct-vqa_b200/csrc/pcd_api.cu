@@ -68,9 +68,10 @@ struct EdgeGeom {
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 // preconditions of the compile-time-tile ("FAST") specialisations: the tile picked for this geometry is one of
-// the fixed ones, tiles are full, every row of every tensor touched starts 16-byte aligned
+// the fixed ones, tiles are full and span the whole image width, every row of every tensor touched starts 16-byte aligned
 static bool fast_ok(const EdgeGeom& q, const Tile& t, bool stageB) {
-    return edge_tile_is_fixed(q.c, q.S, t.TH, t.TW, stageB) && q.Ho % t.TH == 0 && q.Wo % t.TW == 0 && q.Ws % 4 == 0;
+    return edge_tile_is_fixed(q.c, q.S, t.TH, t.TW, stageB) && q.Ho % t.TH == 0 && q.Wo == t.TW && q.Ws == q.S * q.Wo &&
+           q.Hs == q.S * q.Ho && q.Ws % 4 == 0;
 }
 
 static int run_passAB(const EdgeGeom& q, const EdgeF* edges, int n, float eps, void* stream) {

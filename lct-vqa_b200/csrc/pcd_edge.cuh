@@ -95,6 +95,59 @@ PCD_HD void load_tile(float* dst, const float* src, long long cs, int C, int row
     }
 }
 
+// f(i) for i in [0, N): strided over the block's threads, fully unrolled (N is a compile-time constant)
+template <int N, class F>
+PCD_HD void for_tasks(F f) {
+#if PCD_CUDA
+    constexpr int IT = (N + kThreads - 1) / kThreads;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int i = (int)threadIdx.x + it * kThreads;
+        if (N % kThreads == 0 || i < N) f(i);
+    }
+#else
+    for (int i = 0; i < N; ++i) f(i);
+#endif
+}
+// same, rolled (heavy bodies)
+template <int N, class F>
+PCD_HD void for_tasks_rolled(F f) {
+#if PCD_CUDA
+#pragma unroll 1
+    for (int i = (int)threadIdx.x; i < N; i += kThreads) f(i);
+#else
+    for (int i = 0; i < N; ++i) f(i);
+#endif
+}
+
+PCD_HD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+PCD_HD void st4(float* p, float a, float b, float c, float d) {
+    F4 t = {a, b, c, d};
+    *reinterpret_cast<F4*>(p) = t;
+}
+
+// Tile rows that span the full image width W (the compile-time-tile kernels): dst[C][ROWS][W + 8] <- f(ch, src row),
+// image rows gy0 .. gy0 + ROWS - 1 (zero outside the image); the two 4-float column halos are zero padding.
+template <int C, int ROWS, int W, class F>
+PCD_HD void load_rows_full(float* dst, const float* PCD_RESTRICT src, long long cs, int gy0, int H, F f) {
+    constexpr int W4 = W / 4, P = W + 8;
+    static_assert((W4 & (W4 - 1)) == 0, "row width must be a power-of-two number of float4");
+    for_tasks<C * ROWS * W4>([&](int i) {
+        const int x4 = i % W4, row = i / W4, ch = row / ROWS, r = row - ch * ROWS;
+        const int gy = gy0 + r;
+        F4 v = {0.f, 0.f, 0.f, 0.f};
+        if (gy >= 0 && gy < H) {
+            v = ld4(src + ch * cs + (long long)gy * W + 4 * x4);
+            v.x = f(ch, v.x); v.y = f(ch, v.y); v.z = f(ch, v.z); v.w = f(ch, v.w);
+        }
+        *reinterpret_cast<F4*>(dst + row * P + 4 + 4 * x4) = v;
+    });
+    for_tasks<C * ROWS * 2>([&](int i) {
+        const int row = i >> 1;
+        st4(dst + row * P + ((i & 1) ? 4 + W : 0), 0.f, 0.f, 0.f, 0.f);
+    });
+}
+
 // ======================================================================================================
 // forward
 // ======================================================================================================
@@ -196,12 +249,19 @@ PCD_HD void fwdA_body(const PassArgs& a, int bx, int n, int z, float* smem) {
     float* P2 = P + C * NPIX;
     float* WS = P2 + 4 * C * 32;
     const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
-    load_tile<FAST>(XIN, e.x + (long long)n * e.x_ns, (long long)a.Hs * a.Ws, C, IH, IW, S * g.oy0 - 4, S * g.ox0 - 4,
-                    a.Hs, a.Ws, [](int, float v) { return v; });
+    if (FAST) {      // full-width tile; the conv jobs get relu(x) (applied once here), the pool job the raw tile
+        constexpr int FIH = S * (FTH ? FTH : 4) + 8, FW = S * (FTW ? FTW : 4);
+        const float* src = e.x + (long long)n * e.x_ns;
+        if (job < 4) load_rows_full<C, FIH, FW>(XIN, src, (long long)a.Hs * a.Ws, S * g.oy0 - 4, a.Hs, [](int, float v) { return relu(v); });
+        else load_rows_full<C, FIH, FW>(XIN, src, (long long)a.Hs * a.Ws, S * g.oy0 - 4, a.Hs, [](int, float v) { return v; });
+    } else {
+        load_tile<FAST>(XIN, e.x + (long long)n * e.x_ns, (long long)a.Hs * a.Ws, C, IH, IW, S * g.oy0 - 4, S * g.ox0 - 4,
+                        a.Hs, a.Ws, [](int, float v) { return v; });
+    }
     PCD_SYNC();
 
 #define PCD_UNIT_A(U, KS, DIL)                                                                                     \
-    unit_forward<C, KS, DIL, S, true, FAST>(XIN, IH, IW, 4, e.par + edge_dw_off(C, S, U), e.par + edge_pw_off(C, S, U), \
+    unit_forward<C, KS, DIL, S, !FAST, FAST>(XIN, IH, IW, 4, e.par + edge_dw_off(C, S, U), e.par + edge_pw_off(C, S, U), \
                                             T, P, P2, WS, e.saved + slot_t(U) * nslot, e.saved + slot_z(U) * nslot, \
                                             e.stats + bn_unit(S, U) * 2 * C, g)
     if (job == 0) { PCD_UNIT_A(0, 3, 1); return; }
@@ -211,6 +271,55 @@ PCD_HD void fwdA_body(const PassArgs& a, int bx, int n, int z, float* smem) {
 #undef PCD_UNIT_A
 
     // ---- job 4: 3x3 max / avg pool (operations.py:6-7), stride S, pad 1, count_include_pad=False ---------
+    if (FAST) {
+        // full-width tile: the only out-of-image taps are whole rows, the left-most tap of the first pixel of a row
+        // and (stride 1) the right-most tap of the last one; the column halo holds zeros (right for the sums)
+        PCD_FOR(task, C * NSTRIP) {
+            const int ch = task / NSTRIP, strip = task - ch * NSTRIP;
+            const int oyl = strip / PW4, oxl = (strip - oyl * PW4) * 4;
+            const float* pl = XIN + ch * IH * IW;
+            const int oy = g.oy0 + oyl;
+            const bool left = oxl == 0, right = (S == 1) && (oxl + 4 == TW);
+            float mx[4], sm[4];
+            int nrow = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mx[j] = -INFINITY; sm[j] = 0.f; }
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int gy = S * oy + dy - 1;
+                if (gy < 0 || gy >= a.Hs) continue;
+                ++nrow;
+                const F4* rp = reinterpret_cast<const F4*>(pl + (S * oyl + dy + 3) * IW + S * oxl);
+                float v[12];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { const F4 t = rp[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int idx = S * j + dx + 3;
+                        const float val = v[idx];
+                        sm[j] += val;
+                        float vm = val;
+                        if (idx == 3) vm = left ? -INFINITY : val;
+                        if (S == 1 && idx == 8 && j == 3) vm = right ? -INFINITY : val;
+                        mx[j] = vm > mx[j] ? vm : mx[j];
+                    }
+            }
+            float av[4], s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ncol = 3 - ((j == 0 && left) ? 1 : 0) - ((j == 3 && right) ? 1 : 0);
+                av[j] = sm[j] / (float)(nrow * ncol);
+                s1 += mx[j]; q1 = fmaf(mx[j], mx[j], q1);
+                s2 += av[j]; q2 = fmaf(av[j], av[j], q2);
+            }
+            store4<true>(e.saved + slot_p1() * nslot, g, C, ch, oy, oxl, mx);
+            store4<true>(e.saved + slot_p2() * nslot, g, C, ch, oy, oxl, av);
+            const int NT = C * NSTRIP;
+            P[0 * NT + task] = s1; P[1 * NT + task] = q1; P[2 * NT + task] = s2; P[3 * NT + task] = q2;
+        }
+    } else
     PCD_FOR(task, C * NSTRIP) {
         const int ch = task / NSTRIP, strip = task - ch * NSTRIP;
         const int oyl = strip / PW4, oxl = (strip - oyl * PW4) * 4;
@@ -331,9 +440,17 @@ PCD_HD void fwdB_body(const PassArgs& a, int bx, int n, int z, float* smem) {
         BNC[2 * j + 1] = b.rstd;
     }
     PCD_SYNC();
-    load_tile<FAST>(Q, e.saved + slot_z(uA) * nslot + (long long)n * C * a.Ho * a.Wo, (long long)a.Ho * a.Wo, C, IH, IW,
-                    g.oy0 - HY, g.ox0 - 4, a.Ho, a.Wo,
-                    [&](int ch, float v) { return relu((v - BNC[2 * ch]) * BNC[2 * ch + 1]); });
+    {
+        const float* src = e.saved + slot_z(uA) * nslot + (long long)n * C * a.Ho * a.Wo;
+        auto bnrelu = [&](int ch, float v) { return relu((v - BNC[2 * ch]) * BNC[2 * ch + 1]); };
+        if (FAST) {
+            constexpr int FTH_ = FTH ? FTH : 4, FW = FTW ? FTW : 4;
+            if (half == 0) load_rows_full<C, FTH_ + 2, FW>(Q, src, (long long)a.Ho * a.Wo, g.oy0 - 1, a.Ho, bnrelu);
+            else load_rows_full<C, FTH_ + 4, FW>(Q, src, (long long)a.Ho * a.Wo, g.oy0 - 2, a.Ho, bnrelu);
+        } else {
+            load_tile<FAST>(Q, src, (long long)a.Ho * a.Wo, C, IH, IW, g.oy0 - HY, g.ox0 - 4, a.Ho, a.Wo, bnrelu);
+        }
+    }
     PCD_SYNC();
     if (half == 0)
         unit_forward<C, 3, 1, 1, false, FAST>(Q, IH, IW, 1, e.par + edge_dw_off(C, S, uB), e.par + edge_pw_off(C, S, uB), T,

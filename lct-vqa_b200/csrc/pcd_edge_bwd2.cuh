@@ -14,37 +14,6 @@
 
 namespace pcd {
 
-// f(i) for i in [0, N): strided over the block's threads, fully unrolled (N is a compile-time constant)
-template <int N, class F>
-PCD_HD void for_tasks(F f) {
-#if PCD_CUDA
-    constexpr int IT = (N + kThreads - 1) / kThreads;
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-        const int i = (int)threadIdx.x + it * kThreads;
-        if (N % kThreads == 0 || i < N) f(i);
-    }
-#else
-    for (int i = 0; i < N; ++i) f(i);
-#endif
-}
-// same, rolled (heavy bodies)
-template <int N, class F>
-PCD_HD void for_tasks_rolled(F f) {
-#if PCD_CUDA
-#pragma unroll 1
-    for (int i = (int)threadIdx.x; i < N; i += kThreads) f(i);
-#else
-    for (int i = 0; i < N; ++i) f(i);
-#endif
-}
-
-PCD_HD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
-PCD_HD void st4(float* p, float a, float b, float c, float d) {
-    F4 t = {a, b, c, d};
-    *reinterpret_cast<F4*>(p) = t;
-}
-
 // ---- shared building blocks -----------------------------------------------------------------------------
 // DZ[co][r][x] = BN-backward(dy, z) for image rows oyf + r (zero outside the image); full-width rows.
 template <int C, int RH, int TW>
