@@ -252,6 +252,17 @@ int pcd_adaptive_avgpool_forward(const float* x, float* y, int batch, int channe
 int pcd_adaptive_avgpool_backward(const float* gy, float* gx, int batch, int channels, int h, int w,
                                   int oh, int ow, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense fp32 contraction on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor memory):
+ *     C[M][N] = A[M][K] * B[N][K]^T (+ bias[N])        row-major, K contiguous in A and B
+ * Replaces the cuBLAS SGEMMs behind nn.Linear for the question decoder's vocabulary projection
+ * (darts_vqa/vqa_model.py:192-194, fc1 over B*30 rows) and its backward products.
+ * A, B: 16-byte aligned, lda / ldb multiples of 4.  split_k > 1: K is split over blockIdx.z and partial sums are
+ * added atomically into a zeroed C (done here).  bias may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int pcd_gemm_tn_3xtf32(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                       int M, int N, int K, const float* bias, int split_k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

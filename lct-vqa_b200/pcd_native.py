@@ -78,7 +78,8 @@ EXPORTS = ("pcd_launch_count", "pcd_profile_enable", "pcd_profile_num_kernels", 
            "pcd_profile_collect", "pcd_version", "pcd_strerror", "pcd_is_cuda_build", "pcd_last_cuda_error", "pcd_channel_shuffle",
            "pcd_cell_sizes_of", "pcd_cell_forward", "pcd_cell_backward", "pcd_mixedop_sizes_of",
            "pcd_mixedop_forward", "pcd_mixedop_backward", "pcd_stem_forward", "pcd_stem_backward",
-           "pcd_preprocess_forward", "pcd_preprocess_backward", "pcd_adaptive_avgpool_forward", "pcd_adaptive_avgpool_backward")
+           "pcd_preprocess_forward", "pcd_preprocess_backward", "pcd_adaptive_avgpool_forward", "pcd_adaptive_avgpool_backward",
+           "pcd_gemm_tn_3xtf32")
 
 
 def _declare(lib):
@@ -104,6 +105,8 @@ def _declare(lib):
     lib.pcd_preprocess_backward.argtypes = [C.POINTER(PreArgs), vp]
     lib.pcd_adaptive_avgpool_forward.argtypes = [vp, vp] + [C.c_int] * 6 + [vp]
     lib.pcd_adaptive_avgpool_backward.argtypes = [vp, vp] + [C.c_int] * 6 + [vp]
+    lib.pcd_gemm_tn_3xtf32.argtypes = [vp, C.c_longlong, vp, C.c_longlong, vp, C.c_longlong, C.c_int, C.c_int, C.c_int, vp,
+                                       C.c_int, vp]
     return lib
 
 
@@ -160,7 +163,7 @@ def ptr(t):
 
 def profile_collect(lib):
     """-> {kernel name: (total ms, launches)} for the launches recorded since pcd_profile_enable(1)."""
-    n = 64
+    n = 96
     ms = (C.c_double * n)()
     cnt = (C.c_longlong * n)()
     rc = lib.pcd_profile_collect(ms, cnt, n)

@@ -454,3 +454,76 @@ def preprocess_apply(module, x, fr):
     ar = module._pcd_arena.ensure()
     meta = (fr, c_in, c_out, (ar.param_ptr, ar.running_ptr, ar.nbt_ptr))
     return PreprocessFunction.apply(x, meta, *ar.params)
+
+
+# --------------------------------------------------------------------------------------------
+# dense projection on the tcgen05 tensor cores (3xTF32, fp32 accumulation): nn.Linear drop-in
+# --------------------------------------------------------------------------------------------
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _gemm_tn(lib, a, lda, b, ldb, c, ldc, m, n, k, bias, split_k, ref):
+    N.check(lib, lib.pcd_gemm_tn_3xtf32(N.ptr(a), lda, N.ptr(b), ldb, N.ptr(c), ldc, m, n, k, N.ptr(bias), split_k,
+                                        N.stream_for(ref)), "pcd_gemm_tn_3xtf32")
+
+
+class Linear3xTF32Function(torch.autograd.Function):
+    """y = x @ W^T + b through pcd_gemm_tn_3xtf32 (vqa_model.py:192-194 `fc1`, the vocabulary projection).
+
+    The TMA descriptors need 16-byte row pitches: the logits, their gradient and W^T live in buffers whose row pitch
+    is the vocabulary size rounded up to a multiple of 4 (pad columns are zero); y is returned as a view of it.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = N.lib_for(x)
+        x2 = _f32c(x.reshape(-1, x.shape[-1]))
+        w = _f32c(weight)
+        m, k = x2.shape
+        n = w.shape[0]
+        npad = _pad4(n)
+        out = _empty((m, npad), torch.float32, x2.device)
+        _gemm_tn(lib, x2, k, w, k, out, npad, m, n, k, _f32c(bias) if bias is not None else None, 1, x2)
+        ctx.save_for_backward(x2, w)
+        ctx.meta = (x.shape, n, npad, bias is not None)
+        return out[:, :n].view(*x.shape[:-1], n)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w = ctx.saved_tensors
+        xshape, n, npad, has_bias = ctx.meta
+        lib = N.lib_for(x2)
+        m, k = x2.shape
+        g2 = gy.reshape(m, n)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gp = _empty((m, npad), torch.float32, x2.device)        # dL/dy with a 16-byte row pitch
+            gp[:, :n].copy_(g2)
+            if npad != n:
+                gp[:, n:].zero_()
+            wt = _empty((k, npad), torch.float32, x2.device)        # W^T, same pitch
+            wt[:, :n].copy_(w.t())
+            if npad != n:
+                wt[:, n:].zero_()
+            gx2 = _empty((m, k), torch.float32, x2.device)
+            split = max(1, min(32, npad // 1024))                   # long contraction: split K (also shortens the fp32 chains)
+            _gemm_tn(lib, gp, npad, wt, npad, gx2, k, m, k, npad, None, split, x2)
+            gx = gx2.view(xshape)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            gt = g2.t().contiguous()                                # (n, m)
+            if has_bias and ctx.needs_input_grad[2]:
+                gb = gt.sum(1)
+            if ctx.needs_input_grad[1]:
+                xt = x2.t().contiguous()                            # (k, m)
+                gw = _empty((n, k), torch.float32, x2.device)
+                _gemm_tn(lib, gt, m, xt, m, gw, k, n, k, m, None, 1, x2)
+        return gx, gw, gb
+
+
+def linear_3xtf32(x, weight, bias):
+    """nn.Linear forward on the tensor cores when the shapes allow TMA (rows and depth multiples of 4), else F.linear."""
+    m = x.numel() // x.shape[-1]
+    if x.shape[-1] % 4 or m % 4 or not (x.is_cuda or N._emu_lib is not None):
+        return torch.nn.functional.linear(x, weight, bias)
+    return Linear3xTF32Function.apply(x, weight, bias)

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 import config
+from pcd_ops import linear_3xtf32
 from pcdarts.model_search import Network
 
 
@@ -68,7 +69,8 @@ class QstEncoder(nn.Module):
         out, (hidden, cell) = self.lstm(words, (h0, h0))
         feat = torch.cat((hidden, cell), 2).transpose(0, 1)
         feat = self.fc2(self.tanh(feat.reshape(feat.size(0), -1)))
-        return feat, self.fc1(self.tanh(out.transpose(0, 1)))
+        # vocabulary projection (35 GFLOP at B=64): tcgen05 tensor cores, fp32-accurate 3xTF32 split
+        return feat, linear_3xtf32(self.tanh(out.transpose(0, 1)), self.fc1.weight, self.fc1.bias)
 
     def sample(self, prob):
         if self.deterministic:

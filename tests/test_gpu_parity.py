@@ -52,6 +52,25 @@ def test_cell_production_geometry_vs_oracle(cpp, cp, C, red, rp, H, act_only):
     P.cell_vs_oracle(cpp, cp, C, red, rp, 2, H, DEV, act_only=act_only)
 
 
+# tcgen05 3xTF32 projection (nn.Linear drop-in) vs an fp64 reference: forward, dX (split-K), dW, db; ragged tiles
+@pytest.mark.parametrize("M,K,N", [(1920, 512, 17858), (64, 512, 1000), (120, 36, 70), (256, 1024, 512)])
+def test_linear_3xtf32_vs_fp64(M, K, N):
+    import torch.nn.functional as F
+    from pcd_ops import linear_3xtf32
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M // 4, 4, K, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(DEV).requires_grad_(True)
+    G = torch.randn(M // 4, 4, N, generator=g).to(DEV)
+    y = linear_3xtf32(x, w, b)
+    (y * G).sum().backward()
+    xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yr = F.linear(xr, wr, br)
+    (yr * G.double()).sum().backward()
+    for got, ref, name in ((y, yr, "y"), (x.grad, xr.grad, "dx"), (w.grad, wr.grad, "dw"), (b.grad, br.grad, "db")):
+        P.assert_close(got.double(), ref, 5e-5, name)
+
+
 def test_vqa_model_golden():
     P.vqa_case(DEV)
 
