@@ -252,6 +252,14 @@ int pcd_adaptive_avgpool_forward(const float* x, float* y, int batch, int channe
 int pcd_adaptive_avgpool_backward(const float* gy, float* gx, int batch, int channels, int h, int w,
                                   int oh, int ow, void* stream);
 
+/* Overlap of the deferred weight-gradient jobs with the rest of the backward pass.  With overlap on,
+ * pcd_cell_backward enqueues them on a library-owned low-priority stream (forked with an event: no host
+ * synchronisation; CUDA-graph capturable) and returns without joining: grad_params and every buffer passed to that
+ * call must stay alive and unread until pcd_overlap_join(stream) has been enqueued on the consuming stream.
+ * Call pcd_set_overlap outside stream capture.  Default off. */
+int pcd_set_overlap(int on);
+int pcd_overlap_join(void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense fp32 contraction on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor memory):
  *     C[M][N] = A[M][K] * B[N][K]^T (+ bias[N])        row-major, K contiguous in A and B

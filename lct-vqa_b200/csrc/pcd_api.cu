@@ -38,6 +38,40 @@ static int zero_async(void* p, size_t bytes, void* stream) {
     return PCD_OK;
 }
 
+// ---- optional auxiliary stream for work off the critical path (weight-grad jobs) -------------------------------
+struct OverlapState {
+    int on, pending;
+#if PCD_CUDA
+    cudaStream_t aux;
+    cudaEvent_t fork_ev, join_ev;
+#endif
+};
+static OverlapState g_overlap;
+
+static void* overlap_stream() {
+#if PCD_CUDA
+    return g_overlap.on ? (void*)g_overlap.aux : nullptr;
+#else
+    return nullptr;
+#endif
+}
+// aux waits for everything enqueued on `stream` so far
+static int stream_fork(void* stream, void* aux) {
+#if PCD_CUDA
+    if (cudaEventRecord(g_overlap.fork_ev, (cudaStream_t)stream) != cudaSuccess) return PCD_ERR_CUDA;
+    if (cudaStreamWaitEvent((cudaStream_t)aux, g_overlap.fork_ev, 0) != cudaSuccess) return PCD_ERR_CUDA;
+#endif
+    return PCD_OK;
+}
+// `stream` waits for everything enqueued on aux so far
+static int stream_join(void* stream, void* aux) {
+#if PCD_CUDA
+    if (cudaEventRecord(g_overlap.join_ev, (cudaStream_t)aux) != cudaSuccess) return PCD_ERR_CUDA;
+    if (cudaStreamWaitEvent((cudaStream_t)stream, g_overlap.join_ev, 0) != cudaSuccess) return PCD_ERR_CUDA;
+#endif
+    return PCD_OK;
+}
+
 // ---- kernel body adaptors -----------------------------------------------------------------------------
 template <int C> struct KCombine { static constexpr int kMinBlocks = 1; static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
 struct KNorm { static constexpr int kMinBlocks = 1; static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
@@ -332,6 +366,33 @@ int pcd_profile_collect(double* ms, long long* count, int max_kernels) {
     g_state.prof_n = 0;
     return n;
 }
+/* Overlap of the weight-gradient jobs with the rest of the backward pass.  With overlap on, pcd_cell_backward enqueues
+ * its deferred weight-grad jobs on a library-owned low-priority stream (forked from the caller's stream with an event;
+ * no host synchronisation; capturable in a CUDA graph) and returns WITHOUT joining: grad_params, and every buffer
+ * passed to that call, must stay alive and unread until pcd_overlap_join(stream) has been enqueued.  Call
+ * pcd_set_overlap outside any stream capture.  Off by default. */
+int pcd_set_overlap(int on) {
+#if PCD_CUDA
+    if (on && !g_overlap.aux) {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return PCD_ERR_CUDA;
+        if (cudaStreamCreateWithPriority(&g_overlap.aux, cudaStreamNonBlocking, lo) != cudaSuccess) return PCD_ERR_CUDA;
+        if (cudaEventCreateWithFlags(&g_overlap.fork_ev, cudaEventDisableTiming) != cudaSuccess) return PCD_ERR_CUDA;
+        if (cudaEventCreateWithFlags(&g_overlap.join_ev, cudaEventDisableTiming) != cudaSuccess) return PCD_ERR_CUDA;
+    }
+#endif
+    g_overlap.on = on ? 1 : 0;
+    return PCD_OK;
+}
+int pcd_overlap_join(void* stream) {
+    if (!g_overlap.pending) return PCD_OK;
+    g_overlap.pending = 0;
+#if PCD_CUDA
+    return stream_join(stream, (void*)g_overlap.aux);
+#else
+    return PCD_OK;
+#endif
+}
 int pcd_is_cuda_build(void) { return PCD_CUDA; }
 const char* pcd_last_cuda_error(void) { return g_state.last_err; }
 const char* pcd_strerror(int s) {
@@ -505,8 +566,18 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
             PCD_TRY(run_source_grad(sg, stream));
         }
     }
-    for (int g = 0; g < 2; ++g)
-        if (nwq[g]) PCD_TRY(run_edge_wgrad2(wgeo[g], wq[g], nwq[g], eps, stream));
+    // deferred weight-grad jobs: on the auxiliary stream when overlap is on (joined later by pcd_overlap_join: the
+    // caller keeps every buffer of this call alive until then), else right here
+    if (nwq[0] + nwq[1] > 0) {
+        void* ws = stream;
+        if (void* aux = overlap_stream()) {
+            PCD_TRY(stream_fork(stream, aux));
+            g_overlap.pending = 1;
+            ws = aux;
+        }
+        for (int g = 0; g < 2; ++g)
+            if (nwq[g]) PCD_TRY(run_edge_wgrad2(wgeo[g], wq[g], nwq[g], eps, ws));
+    }
     // 4. d softmax(alpha) rows, d beta
     ArchGradArgs ag;
     memset(&ag, 0, sizeof ag);

@@ -79,7 +79,7 @@ EXPORTS = ("pcd_launch_count", "pcd_profile_enable", "pcd_profile_num_kernels", 
            "pcd_cell_sizes_of", "pcd_cell_forward", "pcd_cell_backward", "pcd_mixedop_sizes_of",
            "pcd_mixedop_forward", "pcd_mixedop_backward", "pcd_stem_forward", "pcd_stem_backward",
            "pcd_preprocess_forward", "pcd_preprocess_backward", "pcd_adaptive_avgpool_forward", "pcd_adaptive_avgpool_backward",
-           "pcd_gemm_tn_3xtf32")
+           "pcd_gemm_tn_3xtf32", "pcd_set_overlap", "pcd_overlap_join")
 
 
 def _declare(lib):
@@ -105,6 +105,7 @@ def _declare(lib):
     lib.pcd_preprocess_backward.argtypes = [C.POINTER(PreArgs), vp]
     lib.pcd_adaptive_avgpool_forward.argtypes = [vp, vp] + [C.c_int] * 6 + [vp]
     lib.pcd_adaptive_avgpool_backward.argtypes = [vp, vp] + [C.c_int] * 6 + [vp]
+    lib.pcd_overlap_join.argtypes = [vp]
     lib.pcd_gemm_tn_3xtf32.argtypes = [vp, C.c_longlong, vp, C.c_longlong, vp, C.c_longlong, C.c_int, C.c_int, C.c_int, vp,
                                        C.c_int, vp]
     return lib

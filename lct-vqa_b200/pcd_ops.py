@@ -154,6 +154,27 @@ def weight_grads_enabled():
     return _WEIGHT_GRADS[0]
 
 
+# ---- weight-grad overlap (pcd_set_overlap): buffers of a Cell backward stay alive until the join ----------------
+_OVERLAP = {"on": False, "keep": []}
+
+
+def set_wgrad_overlap(on):
+    """Run the cells' deferred weight-grad jobs on the library's low-priority stream, overlapping the rest of the backward
+    pass.  They are joined at the start of the stem's backward (the last native op of every pass that computes weight
+    grads) or by overlap_join().  Opt-in: used by SearchStep-driven runs."""
+    lib = N.load_cuda()
+    N.check(lib, lib.pcd_set_overlap(1 if on else 0), "pcd_set_overlap")
+    _OVERLAP["on"] = bool(on)
+
+
+def overlap_join(ref):
+    """Make `ref`'s current stream wait for the outstanding weight-grad jobs; release their buffers."""
+    if _OVERLAP["on"] or _OVERLAP["keep"]:
+        lib = N.lib_for(ref)
+        N.check(lib, lib.pcd_overlap_join(N.stream_for(ref)), "pcd_overlap_join")
+        _OVERLAP["keep"].clear()
+
+
 def _f32c(t):
     t = t.detach()
     if t.dtype != torch.float32:
@@ -228,6 +249,8 @@ class CellFunction(torch.autograd.Function):
                           N.ptr(out), N.ptr(saved), N.ptr(stats), N.ptr(gout), N.ptr(gs0), N.ptr(gs1), N.ptr(gw),
                           N.ptr(gw2), N.ptr(gpar), N.ptr(work), N.ptr(bstats), int(need_par), int(need_in))
         N.check(lib, lib.pcd_cell_backward(C.byref(a), N.stream_for(s1)), "pcd_cell_backward")
+        if _OVERLAP["on"] and need_par:        # the aux-stream jobs read all of these until overlap_join()
+            _OVERLAP["keep"].append((s0, s1, w, w2, out, saved, stats, gout, gpar, work, bstats))
         if _DEBUG_KEEP is not None:
             _DEBUG_KEEP.append(dict(cfg=handle.cfg, gout=gout, gs0=gs0, gs1=gs1, work=work, bstats=bstats, gpar=gpar,
                                     s0=s0, s1=s1, saved=saved, stats=stats, w=w, w2=w2, sizes=sz))
@@ -331,6 +354,7 @@ class StemFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("gradient w.r.t. the image is not part of the search path")
         lib = N.lib_for(x)
+        overlap_join(x)
         B, cout, H, W = ctx.meta
         gout = _f32c(gout)
         need_par = any(ctx.needs_input_grad[2:])

@@ -56,7 +56,8 @@ class GraphedSearchStep:
         self.train = [t.clone() for t in train_batch]
         self.valid = [t.clone() for t in valid_batch]
         step.architect.device_scalars = True
-        side = torch.cuda.Stream()
+        # high priority: with weight-grad overlap on, the library's low-priority stream only fills the SMs this one leaves idle
+        side = torch.cuda.Stream(priority=-1)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                 # warm-up on a side stream (allocator, cuDNN/cuBLAS handles)
             for _ in range(warmup):
@@ -64,7 +65,7 @@ class GraphedSearchStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.loss = step.step(self.train, self.valid, lr, unrolled)
 
     def __call__(self, train_batch=None, valid_batch=None):

@@ -52,6 +52,18 @@ def test_cell_production_geometry_vs_oracle(cpp, cp, C, red, rp, H, act_only):
     P.cell_vs_oracle(cpp, cp, C, red, rp, 2, H, DEV, act_only=act_only)
 
 
+def test_w_step_with_wgrad_overlap_matches_golden():
+    """Weight-grad jobs on the library's low-priority stream (joined in the stem backward): same w-step as the golden."""
+    import pcd_ops
+    pcd_ops.set_wgrad_overlap(True)
+    try:
+        P.wstep_case(DEV)
+        P.network_case(DEV)
+    finally:
+        pcd_ops.overlap_join(torch.zeros(1, device=DEV))
+        pcd_ops.set_wgrad_overlap(False)
+
+
 # tcgen05 3xTF32 projection (nn.Linear drop-in) vs an fp64 reference: forward, dX (split-K), dW, db; ragged tiles
 @pytest.mark.parametrize("M,K,N", [(1920, 512, 17858), (64, 512, 1000), (120, 36, 70), (256, 1024, 512)])
 def test_linear_3xtf32_vs_fp64(M, K, N):
