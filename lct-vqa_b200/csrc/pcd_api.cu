@@ -77,13 +77,14 @@ template <int C> struct KCombine { static constexpr int kMinBlocks = 1; static c
 struct KNorm { static constexpr int kMinBlocks = 1; static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
 struct KStem { static constexpr int kMinBlocks = 1; static const char* name() { return "Stem"; } static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
 struct KGapF { static constexpr int kMinBlocks = 1; static const char* name() { return "GapF"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };
-struct KGapB { static constexpr int kMinBlocks = 1; static const char* name() { return "GapB"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_bwd_body(a, x); } };
+struct KGapB { static constexpr int kMinBlocks = 1; static const char* name() { return "GapB"; } static PCD_D void run(const GapArgs& a, int x, int y, int, float*) { gap_bwd_body(a, x, y, a.ny); } };
 struct KShuffle { static constexpr int kMinBlocks = 1; static const char* name() { return "Shuffle"; } static PCD_D void run(const ShuffleArgs& a, int x, int y, int z, float*) { shuffle_body(a, x, y, z); } };
 template <int C> struct KNodeStats { static constexpr int kMinBlocks = 1; static const char* name() { return C == 4 ? "node_stats_c4" : C == 8 ? "node_stats_c8" : "node_stats_c16"; } static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
 struct KSourceGrad { static constexpr int kMinBlocks = 1; static const char* name() { return "SourceGrad"; } static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
 struct KArchGrads { static constexpr int kMinBlocks = 1; static const char* name() { return "ArchGrads"; } static PCD_D void run(const ArchGradArgs& a, int, int, int, float* sm) { arch_grads_body(a, sm); } };
 struct KBnBwdStats { static constexpr int kMinBlocks = 1; static const char* name() { return "BnBwdStats"; } static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
 struct KStemBwd { static constexpr int kMinBlocks = 1; static const char* name() { return "StemBwd"; } static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd_body(a, x, a.nblocks_launch, sm); } };
+struct KStemBwd2 { static constexpr int kMinBlocks = 2; static const char* name() { return "StemBwd"; } static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd2_body(a, x, a.nblocks_launch, sm); } };
 
 #define PCD_DISPATCH_C(c, EXPR)                         \
     do {                                                \
@@ -720,6 +721,11 @@ int pcd_stem_backward(const pcd_stem_args* a, void* stream) {
     b.nblocks_launch = b.nblocks_px < 296 ? b.nblocks_px : 296;
     b.x = a->x; b.z = a->saved_z; b.dy = a->grad_out; b.gamma = a->params + Co * 27; b.stats = a->stats; b.bstats = a->bstats;
     b.eps = a->bn_eps; b.gw = a->grad_params; b.ggamma = a->grad_params + Co * 27; b.gbias = a->grad_params + Co * 28;
+    if (stem_bwd2_ok(Co, a->height, a->width) && !((((uintptr_t)a->x) | ((uintptr_t)a->saved_z) | ((uintptr_t)a->grad_out)) & 15)) {
+        const int ntiles = a->batch * (a->height / kStemTR);
+        b.nblocks_launch = ntiles < 592 ? ntiles : 592;
+        return launch<KStemBwd2, StemBwdArgs>(b, b.nblocks_launch, 1, 1, stem_bwd2_smem_floats(Co, a->width), stream);
+    }
     return launch<KStemBwd, StemBwdArgs>(b, b.nblocks_launch, 1, 1, stem_bwd_smem_floats(Co, 64), stream);
 }
 
@@ -741,7 +747,7 @@ int pcd_preprocess_backward(const pcd_pre_args* a, void* stream) {
 int pcd_adaptive_avgpool_forward(const float* x, float* y, int batch, int channels, int h, int w, int oh, int ow, void* stream) {
     if (!x || !y) return PCD_ERR_ARG;
     GapArgs a;
-    a.B = batch; a.C = channels; a.H = h; a.W = w; a.OH = oh; a.OW = ow; a.x = x; a.y = y;
+    a.B = batch; a.C = channels; a.H = h; a.W = w; a.OH = oh; a.OW = ow; a.ny = 1; a.x = x; a.y = y;
     const long long total = (long long)batch * channels * oh * ow;
     return launch<KGapF, GapArgs>(a, (int)((total + kThreads - 1) / kThreads), 1, 1, 0, stream);
 }
@@ -749,9 +755,10 @@ int pcd_adaptive_avgpool_forward(const float* x, float* y, int batch, int channe
 int pcd_adaptive_avgpool_backward(const float* gy, float* gx, int batch, int channels, int h, int w, int oh, int ow, void* stream) {
     if (!gy || !gx) return PCD_ERR_ARG;
     GapArgs a;
-    a.B = batch; a.C = channels; a.H = h; a.W = w; a.OH = oh; a.OW = ow; a.x = gy; a.y = gx;
-    const long long total = (long long)batch * channels * h * w;
-    return launch<KGapB, GapArgs>(a, (int)((total + kThreads - 1) / kThreads), 1, 1, 0, stream);
+    a.B = batch; a.C = channels; a.H = h; a.W = w; a.OH = oh; a.OW = ow; a.ny = 1; a.x = gy; a.y = gx;
+    const int planes = batch * channels;
+    a.ny = planes < 4096 ? planes : 4096;
+    return launch<KGapB, GapArgs>(a, (h * w + kThreads - 1) / kThreads, a.ny, 1, 0, stream);
 }
 
 }  // extern "C"

@@ -454,4 +454,101 @@ PCD_HD void stem_bwd_body(const StemBwdArgs& a, int bx, int nblk, float* smem) {
     PCD_FOR(i, Cout * 27) pcd_atomic_add(a.gw + i, WACC[i]);
 }
 
+// ---- stem backward, v2: 4-row x full-width tiles, register accumulators across tiles -------------------------------
+// dW[co][ci][ky][kx] = sum_{n,p} dz[co][p] * x[ci][p + (ky-1, kx-1)].  Task = (4 output channels, ci, ky) x pixel part;
+// per float4 strip of pixels: 4 + 3 LDS.128, 48 FMA into 12 accumulators that live in registers over all the block's tiles.
+constexpr int kStemTR = 4;
+PCD_HOSTDEV bool stem_bwd2_ok(int Cout, int H, int W) { return Cout % 4 == 0 && (Cout / 4) * 9 <= kThreads && W % 4 == 0 && W <= 64 && H % kStemTR == 0; }
+PCD_HOSTDEV size_t stem_bwd2_smem_floats(int Cout, int W) {
+    return (size_t)Cout * kStemTR * W + (size_t)3 * (kStemTR + 2) * (W + 8) + 5 * Cout + 16;
+}
+
+PCD_HD void stem_bwd2_body(const StemBwdArgs& a, int bx, int nblk, float* smem) {
+    const int Cout = a.Cout, W = a.W, H = a.H, HW = H * W, NPX = kStemTR * W, W4 = W / 4, XP = W + 8, XR = kStemTR + 2;
+    float* DZ = smem;                         // [Cout][NPX]
+    float* XT = DZ + Cout * NPX;              // [3][XR][XP]   (row halo 1, column halo 4)
+    float* COEF = XT + 3 * XR * XP;
+    float* P = DZ;                            // [12][kThreads] after the tile loop
+    const int ncombo = (Cout / 4) * 9, nparts = kThreads / ncombo;
+    const double cnt = (double)a.B * HW;
+    PCD_FOR(co, Cout) {
+        BnC b = bn_consts(a.stats, Cout, 0, co, cnt, a.eps);
+        COEF[5 * co] = b.rstd * a.gamma[co];
+        COEF[5 * co + 1] = (float)(a.bstats[co] / cnt);
+        COEF[5 * co + 2] = (float)(a.bstats[Cout + co] / cnt);
+        COEF[5 * co + 3] = b.mean;
+        COEF[5 * co + 4] = b.rstd;
+        if (bx == 0) {
+            a.gbias[co] = (float)a.bstats[co];
+            a.ggamma[co] = (float)a.bstats[Cout + co];
+        }
+    }
+    PCD_TSTATE(float, acc, [4][3]);
+    PCD_EACH(task) {
+        auto& ac = PCD_TREF(acc, task);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ac[i][k] = 0.f;
+    }
+    const int tiles_per_img = H / kStemTR, ntiles = a.B * tiles_per_img;
+    for (int tile = bx; tile < ntiles; tile += nblk) {
+        const int n = tile / tiles_per_img, y0 = (tile - n * tiles_per_img) * kStemTR;
+        PCD_SYNC();                           // COEF ready / previous tile's readers done
+        PCD_FOR(i, Cout * NPX / 4) {
+            const int co = i / (NPX / 4), s4 = i - co * (NPX / 4);
+            const long long o = ((long long)n * Cout + co) * HW + (long long)y0 * W + 4 * s4;
+            const F4 z4 = *reinterpret_cast<const F4*>(a.z + o), d4 = *reinterpret_cast<const F4*>(a.dy + o);
+            const float c0 = COEF[5 * co], c1 = COEF[5 * co + 1], c2 = COEF[5 * co + 2], m = COEF[5 * co + 3], r = COEF[5 * co + 4];
+            F4 v = {c0 * (d4.x - c1 - (z4.x - m) * r * c2), c0 * (d4.y - c1 - (z4.y - m) * r * c2),
+                    c0 * (d4.z - c1 - (z4.z - m) * r * c2), c0 * (d4.w - c1 - (z4.w - m) * r * c2)};
+            *reinterpret_cast<F4*>(DZ + co * NPX + 4 * s4) = v;
+        }
+        PCD_FOR(i, 3 * XR * (XP / 4)) {
+            const int c4 = i % (XP / 4), rr = i / (XP / 4), r = rr % XR, ci = rr / XR;
+            const int gy = y0 - 1 + r, gx = 4 * c4 - 4;
+            F4 v = {0.f, 0.f, 0.f, 0.f};
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = *reinterpret_cast<const F4*>(a.x + ((long long)n * 3 + ci) * HW + (long long)gy * W + gx);
+            *reinterpret_cast<F4*>(XT + (ci * XR + r) * XP + 4 * c4) = v;
+        }
+        PCD_SYNC();
+        PCD_EACH(task) {
+            const int combo = task / nparts, part = task - combo * nparts;
+            if (combo < ncombo) {
+                auto& ac = PCD_TREF(acc, task);
+                const int co0 = (combo / 9) * 4, cik = combo % 9, ci = cik / 3, ky = cik - ci * 3;
+                for (int st = part; st < NPX / 4; st += nparts) {
+                    const int r = st / W4, x4 = st - r * W4;
+                    const float* xr = XT + (ci * XR + r + ky) * XP + 4 * x4;
+                    const F4 a0 = *reinterpret_cast<const F4*>(xr), a1 = *reinterpret_cast<const F4*>(xr + 4), a2 = *reinterpret_cast<const F4*>(xr + 8);
+                    const float v[6] = {a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};        // image columns 4*x4 - 1 .. 4*x4 + 4
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const F4 d = *reinterpret_cast<const F4*>(DZ + (co0 + i) * NPX + 4 * st);
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+                            ac[i][kx] = fmaf(d.x, v[kx], fmaf(d.y, v[kx + 1], fmaf(d.z, v[kx + 2], fmaf(d.w, v[kx + 3], ac[i][kx]))));
+                    }
+                }
+            }
+        }
+    }
+    PCD_SYNC();
+    PCD_EACH(task) {
+        auto& ac = PCD_TREF(acc, task);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) P[(i * 3 + k) * kThreads + task] = ac[i][k];
+    }
+    PCD_SYNC();
+    PCD_FOR(q, ncombo * 12) {
+        const int combo = q / 12, ik = q - combo * 12, i = ik / 3, kx = ik - i * 3;
+        float s = 0.f;
+        for (int part = 0; part < nparts; ++part) s += P[ik * kThreads + combo * nparts + part];
+        const int co = (combo / 9) * 4 + i, cik = combo % 9;
+        pcd_atomic_add(a.gw + co * 27 + cik * 3 + kx, s);
+    }
+}
+
 }  // namespace pcd

@@ -36,6 +36,19 @@ namespace pcd {
 struct alignas(16) F4 { float x, y, z, w; };
 
 constexpr int kThreads = 256;
+}  // namespace pcd
+
+// Thread-private state that must survive a barrier: one copy per emulated thread in the CPU emulation build
+#if PCD_CUDA
+#define PCD_TSTATE(type, name, dims) type name dims
+#define PCD_TREF(name, tid) name
+#else
+#define PCD_TSTATE(type, name, dims) type name##_all[pcd::kThreads] dims
+#define PCD_TREF(name, tid) name##_all[tid]
+#endif
+#define PCD_EACH(task) PCD_FOR(task, pcd::kThreads)
+
+namespace pcd {
 constexpr int kMaxEdgesPerLaunch = 8;
 constexpr int kUnits = 6;
 constexpr int PCD_MAX_EDGES_CONST = 14;   // A3 B3 A5 B5 D3 D5  (sep3 first/second half, sep5, dil3, dil5)

@@ -445,12 +445,15 @@ PCD_HOSTDEV size_t wgrad2_smem_floats() {
 // unit with input stride SI (1 for the second halves), kernel KS, dilation DIL; BNIN: the unit input is relu(bn(zA)).
 // The input tile keeps only the LEFT 4-float column halo: rows are full image width, so the right halo of row r is
 // the (zero) left halo of row r + 1 (pitch = width + 4; 4 zero floats follow the last row).
+// One block walks every tile of images [n0, n1): the weight-grad partial sums stay in registers across tiles and are
+// reduced over the block (and added atomically) once.
 template <int C, int SI, int KS, int DIL, int TH, int TW, bool BNIN>
-PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, int u, float* smem) {
+PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, int n0, int n1, int u, float* smem) {
     constexpr int PAD = DIL * (KS - 1) / 2, NPIX = TH * TW, PW4 = TW / 4, NPATCH = (TH / 4) * PW4;
     constexpr int IH = SI * TH + 8, XW = SI * TW + 4;
     constexpr int NOG = (C / 4) * (C / 4), NTP = 256, NSL = NTP / NOG;     // pointwise: 4x4 outputs x pixel slices
     static_assert((NPIX / 4) % NSL == 0, "pointwise slices");
+    static_assert(C * NPATCH <= kThreads && NTP <= kThreads, "one task per thread");
     const int S = a.S;
     float* DZ = smem;                       // [C][NPIX]
     float* T = DZ + C * NPIX;               // [C][NPIX]   saved depthwise output
@@ -461,7 +464,7 @@ PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, 
     float* COEF = P2 + 25 * C * 4 + 16 * 16 * 4;
     float* BNA = COEF + 4 * C;
     float* WT = BNA + 2 * C;
-    float* Pdw = DZ;                        // [KS*KS][C*NPATCH] (DZ, T are dead by then)
+    float* Pdw = DZ;                        // [KS*KS][C*NPATCH] (after the tile loop)
     const long long nslot = (long long)a.B * C * a.Ho * a.Wo, HW = (long long)a.Ho * a.Wo;
     const double cnt = (double)a.B * a.Ho * a.Wo;
     const float beta = e.beta ? e.beta[0] : 1.f;
@@ -482,15 +485,31 @@ PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, 
         }
     }
     PCD_FOR(i, C * C) WT[(i % C) * C + i / C] = w_pw[i];
-    PCD_SYNC();
-    // ---- tiles: unit input (haloed), saved depthwise output, dz --------------------------------------------
-    {
-        const float* src = BNIN ? e.saved + slot_z(u - 1) * nslot + (long long)g.n * C * HW : e.x + (long long)g.n * e.x_ns;
-        const int H = BNIN ? a.Ho : a.Hs, W = BNIN ? a.Wo : a.Ws;
-        const long long scs = (long long)H * W;
+    PCD_FOR(i, 4) IN[(size_t)C * IH * XW + i] = 0.f;
+    PCD_TSTATE(float, accp, [4][4]);
+    PCD_TSTATE(float, accd, [KS * KS]);
+    PCD_EACH(task) {
+        auto& ap = PCD_TREF(accp, task);
+        auto& ad = PCD_TREF(accd, task);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ap[i][k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KS * KS; ++k) ad[k] = 0.f;
+    }
+    const int H = BNIN ? a.Ho : a.Hs, W = BNIN ? a.Wo : a.Ws;
+    const long long scs = (long long)H * W;
+    const int tiles = a.Ho / TH;
+    for (int n = n0; n < n1; ++n)
+    for (int tile = 0; tile < tiles; ++tile) {
+        const int oy0 = tile * TH;
+        PCD_SYNC();                               // constants ready / previous tile's readers are done
+        // ---- tiles: unit input (haloed), saved depthwise output, dz ----------------------------------------
+        const float* src = BNIN ? e.saved + slot_z(u - 1) * nslot + (long long)n * C * HW : e.x + (long long)n * e.x_ns;
         for_tasks<C * IH * (XW / 4)>([&](int i) {
             const int c4 = i % (XW / 4), r = (i / (XW / 4)) % IH, ch = i / ((XW / 4) * IH);
-            const int gy = SI * g.oy0 - 4 + r, gx = 4 * c4 - 4;
+            const int gy = SI * oy0 - 4 + r, gx = 4 * c4 - 4;
             F4 v = {0.f, 0.f, 0.f, 0.f};
             if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
                 v = ld4(src + ch * scs + (long long)gy * W + gx);
@@ -503,64 +522,67 @@ PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, 
             }
             *reinterpret_cast<F4*>(IN + (size_t)i * 4) = v;
         });
-        PCD_FOR(i, 4) IN[(size_t)C * IH * XW + i] = 0.f;
-        const float* tsl = e.saved + slot_t(u) * nslot + (long long)g.n * C * HW + (long long)g.oy0 * TW;
+        const float* tsl = e.saved + slot_t(u) * nslot + (long long)n * C * HW + (long long)oy0 * TW;
         for_tasks<C * NPIX / 4>([&](int i) {
             const int p4 = i % (NPIX / 4), ch = i / (NPIX / 4);
             *reinterpret_cast<F4*>(T + (size_t)i * 4) = ld4(tsl + (long long)ch * HW + 4 * p4);
         });
-        const float* dy_img = isA ? e.ga + which * nslot + (long long)g.n * C * HW : e.dn + (long long)g.n * e.dn_ns;
-        dz_rows<C, TH, TW>(DZ, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)g.n * C * HW, HW, COEF, g.oy0, a.Ho);
+        const float* dy_img = isA ? e.ga + which * nslot + (long long)n * C * HW : e.dn + (long long)n * e.dn_ns;
+        dz_rows<C, TH, TW>(DZ, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)n * C * HW, HW, COEF, oy0, a.Ho);
+        PCD_SYNC();
+        // ---- dt on the centre; pointwise weight-grad partials ---------------------------------------------------
+        dt_rows<C, TH, TW, TW, 0>(DT, DZ, WT, oy0, a.Ho);
+        PCD_EACH(task) {
+            auto& acc = PCD_TREF(accp, task);
+            const int og = task / NSL, sl = task - og * NSL;
+            const int co0 = (og / (C / 4)) * 4, ci0 = (og % (C / 4)) * 4;
+#pragma unroll 2
+            for (int st = sl; st < NPIX / 4; st += NSL) {
+                F4 tv[4], dz[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tv[k] = ld4(T + (ci0 + k) * NPIX + st * 4);
+                    dz[k] = ld4(DZ + (co0 + k) * NPIX + st * 4);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        acc[i][k] = fmaf(dz[i].x, tv[k].x, fmaf(dz[i].y, tv[k].y, fmaf(dz[i].z, tv[k].z, fmaf(dz[i].w, tv[k].w, acc[i][k]))));
+            }
+        }
+        PCD_SYNC();
+        // ---- depthwise weight-grad partials ---------------------------------------------------------------------------
+        PCD_EACH(task) {
+            if (task < C * NPATCH) {
+                auto& acc = PCD_TREF(accd, task);
+                const int ch = task / NPATCH, patch = task - ch * NPATCH;
+                const int py = (patch / PW4) * 4, px = (patch % PW4) * 4;
+                float dt[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const F4 v = ld4(DT + (ch * TH + py + i) * TW + px);
+                    dt[i][0] = v.x; dt[i][1] = v.y; dt[i][2] = v.z; dt[i][3] = v.w;
+                }
+                dw_wgrad_patch<KS, DIL, SI, false>(IN + ch * IH * XW, XW, SI * py - PAD + 4, SI * px, dt, acc);
+            }
+        }
     }
     PCD_SYNC();
-    // ---- dt on the centre; pointwise weight-grad partials ---------------------------------------------------
-    dt_rows<C, TH, TW, TW, 0>(DT, DZ, WT, g.oy0, a.Ho);
-    for_tasks_rolled<NTP>([&](int task) {
-        const int og = task / NSL, sl = task - og * NSL;
-        const int co0 = (og / (C / 4)) * 4, ci0 = (og % (C / 4)) * 4;
-        float acc[4][4];
+    // ---- block reductions (P aliases DZ | T), 4 partials per output, then atomics ---------------------------------------
+    PCD_EACH(task) {
+        auto& ap = PCD_TREF(accp, task);
+        auto& ad = PCD_TREF(accd, task);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
-#pragma unroll 2
-        for (int st = sl; st < NPIX / 4; st += NSL) {
-            F4 tv[4], dz[4];
+            for (int k = 0; k < 4; ++k) Ppw[(i * 4 + k) * NTP + task] = ap[i][k];
+        if (task < C * NPATCH) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                tv[k] = ld4(T + (ci0 + k) * NPIX + st * 4);
-                dz[k] = ld4(DZ + (co0 + k) * NPIX + st * 4);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    acc[i][k] = fmaf(dz[i].x, tv[k].x, fmaf(dz[i].y, tv[k].y, fmaf(dz[i].z, tv[k].z, fmaf(dz[i].w, tv[k].w, acc[i][k]))));
+            for (int k = 0; k < KS * KS; ++k) Pdw[k * (C * NPATCH) + task] = ad[k];
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) Ppw[(i * 4 + k) * NTP + task] = acc[i][k];
-    });
+    }
     PCD_SYNC();
-    // ---- depthwise weight-grad partials (P aliases DZ | T) ------------------------------------------------------
-    for_tasks_rolled<C * NPATCH>([&](int task) {
-        const int ch = task / NPATCH, patch = task - ch * NPATCH;
-        const int py = (patch / PW4) * 4, px = (patch % PW4) * 4;
-        float dt[4][4], acc[KS * KS];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const F4 v = ld4(DT + (ch * TH + py + i) * TW + px);
-            dt[i][0] = v.x; dt[i][1] = v.y; dt[i][2] = v.z; dt[i][3] = v.w;
-        }
-#pragma unroll
-        for (int k = 0; k < KS * KS; ++k) acc[k] = 0.f;
-        dw_wgrad_patch<KS, DIL, SI, false>(IN + ch * IH * XW, XW, SI * py - PAD + 4, SI * px, dt, acc);
-#pragma unroll
-        for (int k = 0; k < KS * KS; ++k) Pdw[k * (C * NPATCH) + task] = acc[k];
-    });
-    PCD_SYNC();
-    // ---- block reductions, 4 partials per output, then atomics ----------------------------------------------------
     constexpr int NP = 4, NDW = KS * KS * C, NPW = 16 * NOG;
     float* P2dw = P2;
     float* P2pw = P2 + 25 * C * 4;
@@ -658,21 +680,31 @@ PCD_HD void wgrad2_fr_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, fl
     });
 }
 
+constexpr int kWgradImages = 4;      // images per weight-grad block
+
 template <int C, int S, int TH, int TW>
-PCD_HD void wgrad2_body(const EdgeBwdArgs& a, int bx, int n, int z, float* smem) {
+PCD_HD void wgrad2_body(const EdgeBwdArgs& a, int bx, int by, int z, float* smem) {
     constexpr int NJ = 6 + (S == 2);
     const int ez = z / NJ, job = z - ez * NJ;
     const EdgeG& e = a.e[ez];
-    Geo g;
-    g.n = n; g.TH = TH; g.TW = TW; g.Ho = a.Ho; g.Wo = a.Wo;
-    g.oy0 = bx * TH; g.ox0 = 0;
-    if (job == 0) wgrad2_unit_job<C, S, 3, 1, TH, TW, false>(a, e, g, 0, smem);
-    else if (job == 1) wgrad2_unit_job<C, 1, 3, 1, TH, TW, true>(a, e, g, 1, smem);
-    else if (job == 2) wgrad2_unit_job<C, S, 5, 1, TH, TW, false>(a, e, g, 2, smem);
-    else if (job == 3) wgrad2_unit_job<C, 1, 5, 1, TH, TW, true>(a, e, g, 3, smem);
-    else if (job == 4) wgrad2_unit_job<C, S, 3, 2, TH, TW, false>(a, e, g, 4, smem);
-    else if (job == 5) wgrad2_unit_job<C, S, 5, 2, TH, TW, false>(a, e, g, 5, smem);
-    else if (S == 2) wgrad2_fr_job<C, TH, TW>(a, e, g, smem);
+    const int n0 = by * kWgradImages, n1 = (n0 + kWgradImages < a.B) ? n0 + kWgradImages : a.B;
+    (void)bx;
+    if (job == 0) wgrad2_unit_job<C, S, 3, 1, TH, TW, false>(a, e, n0, n1, 0, smem);
+    else if (job == 1) wgrad2_unit_job<C, 1, 3, 1, TH, TW, true>(a, e, n0, n1, 1, smem);
+    else if (job == 2) wgrad2_unit_job<C, S, 5, 1, TH, TW, false>(a, e, n0, n1, 2, smem);
+    else if (job == 3) wgrad2_unit_job<C, 1, 5, 1, TH, TW, true>(a, e, n0, n1, 3, smem);
+    else if (job == 4) wgrad2_unit_job<C, S, 3, 2, TH, TW, false>(a, e, n0, n1, 4, smem);
+    else if (job == 5) wgrad2_unit_job<C, S, 5, 2, TH, TW, false>(a, e, n0, n1, 5, smem);
+    else if (S == 2) {
+        for (int n = n0; n < n1; ++n)
+            for (int tile = 0; tile < a.Ho / TH; ++tile) {
+                Geo g;
+                g.n = n; g.TH = TH; g.TW = TW; g.Ho = a.Ho; g.Wo = a.Wo;
+                g.oy0 = tile * TH; g.ox0 = 0;
+                PCD_SYNC();
+                wgrad2_fr_job<C, TH, TW>(a, e, g, smem);
+            }
+    }
 }
 
 }  // namespace pcd

@@ -312,7 +312,7 @@ PCD_HD void stem_conv_body(const StemArgs& a, int bx, int n, float* smem) {
 
 // ---- AdaptiveAvgPool2d (model_search.py:129,176) -----------------------------------------------------
 struct GapArgs {
-    int B, C, H, W, OH, OW;
+    int B, C, H, W, OH, OW, ny;      // ny: planes are strided over gridDim.y (backward)
     const float* x;
     float* y;
 };
@@ -335,25 +335,35 @@ PCD_HD void gap_fwd_body(const GapArgs& a, int bx) {
 }
 
 // gx[nc][y][x] = sum over output windows containing (y,x) of gy / window size
-PCD_HD void gap_bwd_body(const GapArgs& a /* x = gy (OHxOW), y = gx (HxW) */, int bx) {
-    const long long total = (long long)a.B * a.C * a.H * a.W;
+// block (bx, by): pixels bx*256.. of planes by, by + nplanes_stride, ...  (32-bit index arithmetic only)
+PCD_HD void gap_bwd_body(const GapArgs& a /* x = gy (OHxOW), y = gx (HxW) */, int bx, int by, int ny) {
+    const int HW = a.H * a.W, planes = a.B * a.C;
     PCD_FOR(t, kThreads) {
-        const long long i = (long long)bx * kThreads + t;
-        if (i < total) {
-            const int x = (int)(i % a.W), y = (int)((i / a.W) % a.H);
-            const long long nc = i / (a.W * a.H);
-            float s = 0.f;
+        const int p = bx * kThreads + t;
+        if (p < HW) {
+            const int y = p / a.W, x = p - y * a.W;
             const int oyc = (y * a.OH) / a.H, oxc = (x * a.OW) / a.W;     // windows overlap by at most one neighbour
+            int oyA = -1, oyB = -1, hyA = 1, hyB = 1, oxA = -1, oxB = -1, hxA = 1, hxB = 1;
             for (int oy = (oyc > 0 ? oyc - 1 : 0); oy <= oyc + 1 && oy < a.OH; ++oy) {
                 const int y0 = (oy * a.H) / a.OH, y1 = ((oy + 1) * a.H + a.OH - 1) / a.OH;
                 if (y < y0 || y >= y1) continue;
-                for (int ox = (oxc > 0 ? oxc - 1 : 0); ox <= oxc + 1 && ox < a.OW; ++ox) {
-                    const int x0 = (ox * a.W) / a.OW, x1 = ((ox + 1) * a.W + a.OW - 1) / a.OW;
-                    if (x < x0 || x >= x1) continue;
-                    s += a.x[(nc * a.OH + oy) * a.OW + ox] / (float)((y1 - y0) * (x1 - x0));
-                }
+                if (oyA < 0) { oyA = oy; hyA = y1 - y0; } else if (oyB < 0) { oyB = oy; hyB = y1 - y0; }
             }
-            a.y[i] = s;
+            for (int ox = (oxc > 0 ? oxc - 1 : 0); ox <= oxc + 1 && ox < a.OW; ++ox) {
+                const int x0 = (ox * a.W) / a.OW, x1 = ((ox + 1) * a.W + a.OW - 1) / a.OW;
+                if (x < x0 || x >= x1) continue;
+                if (oxA < 0) { oxA = ox; hxA = x1 - x0; } else if (oxB < 0) { oxB = ox; hxB = x1 - x0; }
+            }
+            const float dAA = (float)(hyA * hxA), dAB = (float)(hyA * hxB), dBA = (float)(hyB * hxA), dBB = (float)(hyB * hxB);
+            for (int nc = by; nc < planes; nc += ny) {
+                const float* g = a.x + (long long)nc * a.OH * a.OW;
+                float s = 0.f;                 // same order as a scan over (oy, ox)
+                if (oyA >= 0 && oxA >= 0) s += g[oyA * a.OW + oxA] / dAA;
+                if (oyA >= 0 && oxB >= 0) s += g[oyA * a.OW + oxB] / dAB;
+                if (oyB >= 0 && oxA >= 0) s += g[oyB * a.OW + oxA] / dBA;
+                if (oyB >= 0 && oxB >= 0) s += g[oyB * a.OW + oxB] / dBB;
+                a.y[(long long)nc * HW + p] = s;
+            }
         }
     }
 }

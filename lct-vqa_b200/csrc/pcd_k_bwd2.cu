@@ -62,14 +62,18 @@ int launch_bwdA2(const EdgeBwdArgs& a, int c, int gz, void* stream) {
     }
     return PCD_ERR_UNSUPPORTED;
 }
+template <class K>
+static int go_w(const EdgeBwdArgs& a, int gz, size_t smem_floats, void* stream) {
+    return launch<K, EdgeBwdArgs>(a, 1, (a.B + kWgradImages - 1) / kWgradImages, gz, smem_floats, stream);
+}
 int launch_wgrad2(const EdgeBwdArgs& a, int c, int gz, void* stream) {
     if (a.S == 1) {
-        if (c == 4 && a.TH == 16 && a.TW == 64) return go2<KWgrad2<4, 1, 16, 64>>(a, gz, wgrad2_smem_floats<4, 1, 16, 64>(), stream);
-        if (c == 8 && a.TH == 16 && a.TW == 32) return go2<KWgrad2<8, 1, 16, 32>>(a, gz, wgrad2_smem_floats<8, 1, 16, 32>(), stream);
-        if (c == 16 && a.TH == 16 && a.TW == 16) return go2<KWgrad2<16, 1, 16, 16>>(a, gz, wgrad2_smem_floats<16, 1, 16, 16>(), stream);
+        if (c == 4 && a.TH == 16 && a.TW == 64) return go_w<KWgrad2<4, 1, 16, 64>>(a, gz, wgrad2_smem_floats<4, 1, 16, 64>(), stream);
+        if (c == 8 && a.TH == 16 && a.TW == 32) return go_w<KWgrad2<8, 1, 16, 32>>(a, gz, wgrad2_smem_floats<8, 1, 16, 32>(), stream);
+        if (c == 16 && a.TH == 16 && a.TW == 16) return go_w<KWgrad2<16, 1, 16, 16>>(a, gz, wgrad2_smem_floats<16, 1, 16, 16>(), stream);
     } else {
-        if (c == 8 && a.TH == 8 && a.TW == 32) return go2<KWgrad2<8, 2, 8, 32>>(a, gz, wgrad2_smem_floats<8, 2, 8, 32>(), stream);
-        if (c == 16 && a.TH == 8 && a.TW == 16) return go2<KWgrad2<16, 2, 8, 16>>(a, gz, wgrad2_smem_floats<16, 2, 8, 16>(), stream);
+        if (c == 8 && a.TH == 8 && a.TW == 32) return go_w<KWgrad2<8, 2, 8, 32>>(a, gz, wgrad2_smem_floats<8, 2, 8, 32>(), stream);
+        if (c == 16 && a.TH == 8 && a.TW == 16) return go_w<KWgrad2<16, 2, 8, 16>>(a, gz, wgrad2_smem_floats<16, 2, 8, 16>(), stream);
     }
     return PCD_ERR_UNSUPPORTED;
 }

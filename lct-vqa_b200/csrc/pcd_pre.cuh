@@ -18,14 +18,6 @@
 
 namespace pcd {
 
-#if PCD_CUDA
-#define PCD_TSTATE(type, name, dims) type name dims
-#define PCD_TREF(name, tid) name
-#else
-#define PCD_TSTATE(type, name, dims) type name##_all[kThreads] dims
-#define PCD_TREF(name, tid) name##_all[tid]
-#endif
-#define PCD_EACH(task) PCD_FOR(task, kThreads)
 
 struct PreArgs {
     int B, Cin, Cout, Hin, Win, Ho, Wo, fr;   // fr: 1 => FactorizedReduce (Ho = Hin/2)
