@@ -271,6 +271,21 @@ int pcd_overlap_join(void* stream);
 int pcd_gemm_tn_3xtf32(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
                        int M, int N, int K, const float* bias, int split_k, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Cross-entropy over the vocabulary logits, in the padded-pitch layout the projection GEMM writes
+ * (darts_vqa/vqa_model.py:356-358: CE(qst_out[:, :-1], qst[:, 1:]); rows with a negative target are ignored).
+ *   forward : lse[r] = logsumexp(logits[r, :V]);  loss_rows[r] = lse[r] - logits[r, target[r]]  (0 if ignored)
+ *   backward: dlogits[r, c] = scale * (softmax(logits[r])[c] - [c == target[r]])  (0 for ignored rows and pad columns);
+ *             `scale` is a device scalar (upstream grad / number of valid rows)
+ * pcd_transpose_pad: dst[c][r] = src[r][c] (r < R, c < C), dst columns [R, ld_d) zero — the K-major operands of the
+ * backward GEMMs (dlogits^T, W^T, h^T).
+ * ---------------------------------------------------------------------------------------------- */
+int pcd_ce_forward(const float* logits, long long ld, int M, int V, const long long* targets, float* lse,
+                   float* loss_rows, void* stream);
+int pcd_ce_backward(const float* logits, long long ld, int M, int V, const long long* targets, const float* lse,
+                    const float* scale, float* dlogits, void* stream);
+int pcd_transpose_pad(const float* src, long long ld_s, int R, int C, float* dst, long long ld_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

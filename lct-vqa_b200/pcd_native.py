@@ -79,7 +79,8 @@ EXPORTS = ("pcd_launch_count", "pcd_profile_enable", "pcd_profile_num_kernels", 
            "pcd_cell_sizes_of", "pcd_cell_forward", "pcd_cell_backward", "pcd_mixedop_sizes_of",
            "pcd_mixedop_forward", "pcd_mixedop_backward", "pcd_stem_forward", "pcd_stem_backward",
            "pcd_preprocess_forward", "pcd_preprocess_backward", "pcd_adaptive_avgpool_forward", "pcd_adaptive_avgpool_backward",
-           "pcd_gemm_tn_3xtf32", "pcd_set_overlap", "pcd_overlap_join")
+           "pcd_gemm_tn_3xtf32", "pcd_set_overlap", "pcd_overlap_join", "pcd_ce_forward", "pcd_ce_backward",
+           "pcd_transpose_pad")
 
 
 def _declare(lib):
@@ -106,6 +107,9 @@ def _declare(lib):
     lib.pcd_adaptive_avgpool_forward.argtypes = [vp, vp] + [C.c_int] * 6 + [vp]
     lib.pcd_adaptive_avgpool_backward.argtypes = [vp, vp] + [C.c_int] * 6 + [vp]
     lib.pcd_overlap_join.argtypes = [vp]
+    lib.pcd_ce_forward.argtypes = [vp, C.c_longlong, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.pcd_ce_backward.argtypes = [vp, C.c_longlong, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    lib.pcd_transpose_pad.argtypes = [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_longlong, vp]
     lib.pcd_gemm_tn_3xtf32.argtypes = [vp, C.c_longlong, vp, C.c_longlong, vp, C.c_longlong, C.c_int, C.c_int, C.c_int, vp,
                                        C.c_int, vp]
     return lib

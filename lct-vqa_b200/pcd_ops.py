@@ -551,3 +551,72 @@ def linear_3xtf32(x, weight, bias):
     if x.shape[-1] % 4 or m % 4 or not (x.is_cuda or N._emu_lib is not None):
         return torch.nn.functional.linear(x, weight, bias)
     return Linear3xTF32Function.apply(x, weight, bias)
+
+
+def _transpose_pad(lib, src, ld_s, rows, cols, ld_d, ref):
+    """(cols, ld_d) buffer with dst[c][r] = src[r][c]; columns >= rows are zero."""
+    dst = _empty((cols, ld_d), torch.float32, ref.device)
+    N.check(lib, lib.pcd_transpose_pad(N.ptr(src), ld_s, rows, cols, N.ptr(dst), ld_d, N.stream_for(ref)), "pcd_transpose_pad")
+    return dst
+
+
+class VocabCrossEntropyFunction(torch.autograd.Function):
+    """mean_r CE(x_r @ W^T + b, target_r) over the rows with target >= 0  — the question-decoder loss
+    (vqa_model.py:192-194 + 356-358) without ever slicing or re-laying-out the (B*T, V) logits: projection on the
+    tensor cores into a 16-byte-pitch buffer, row statistics and the loss from it, gradient written in the same layout,
+    transposed once for the K-major operand of dW."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, targets):
+        lib = N.lib_for(x)
+        x2 = _f32c(x.reshape(-1, x.shape[-1]))
+        w = _f32c(weight)
+        m, k = x2.shape
+        v = w.shape[0]
+        vp = _pad4(v)
+        tg = targets.reshape(-1).contiguous()
+        logits = _empty((m, vp), torch.float32, x2.device)
+        _gemm_tn(lib, x2, k, w, k, logits, vp, m, v, k, _f32c(bias) if bias is not None else None, 1, x2)
+        lse = _empty(m, torch.float32, x2.device)
+        rows = _empty(m, torch.float32, x2.device)
+        N.check(lib, lib.pcd_ce_forward(N.ptr(logits), vp, m, v, N.ptr(tg), N.ptr(lse), N.ptr(rows), N.stream_for(x2)), "pcd_ce_forward")
+        nvalid = (tg >= 0).sum().clamp_min(1).to(torch.float32)
+        ctx.save_for_backward(x2, w, logits, lse, tg, nvalid)
+        ctx.meta = (x.shape, v, vp, bias is not None)
+        return rows.sum() / nvalid
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w, logits, lse, tg, nvalid = ctx.saved_tensors
+        xshape, v, vp, has_bias = ctx.meta
+        lib = N.lib_for(x2)
+        m, k = x2.shape
+        scale = (g / nvalid).to(torch.float32).reshape(1).contiguous()
+        dl = _empty((m, vp), torch.float32, x2.device)
+        N.check(lib, lib.pcd_ce_backward(N.ptr(logits), vp, m, v, N.ptr(tg), N.ptr(lse), N.ptr(scale), N.ptr(dl),
+                                         N.stream_for(x2)), "pcd_ce_backward")
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = _transpose_pad(lib, w, k, v, k, vp, x2)                     # W^T (k, vp)
+            gx2 = _empty((m, k), torch.float32, x2.device)
+            _gemm_tn(lib, dl, vp, wt, vp, gx2, k, m, k, vp, None, max(1, min(32, vp // 1024)), x2)
+            gx = gx2.view(xshape)
+        need_b = has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            mp = _pad4(m)
+            dlt = _transpose_pad(lib, dl, vp, m, v, mp, x2)                  # dlogits^T (v, mp)
+            if need_b:
+                gb = dlt.sum(1)
+            if ctx.needs_input_grad[1]:
+                xt = _transpose_pad(lib, x2, k, m, k, mp, x2)                # h^T (k, mp)
+                gw = _empty((v, k), torch.float32, x2.device)
+                _gemm_tn(lib, dlt, mp, xt, mp, gw, k, v, k, mp, None, 1, x2)
+        return gx, gw, gb, None
+
+
+def vocab_cross_entropy(x, weight, bias, targets):
+    """Fused projection + cross-entropy (ignore target < 0, mean over the rest); plain torch when TMA cannot take the shape."""
+    if x.shape[-1] % 4 or not (x.is_cuda or N._emu_lib is not None):
+        logits = torch.nn.functional.linear(x, weight, bias)
+        return torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), targets.reshape(-1), ignore_index=-100)
+    return VocabCrossEntropyFunction.apply(x, weight, bias, targets)

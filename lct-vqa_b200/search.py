@@ -22,9 +22,7 @@ class SearchStep:
     def w_step(self, image, question, label):
         """experiment.py:187-200."""
         self.optimizer.zero_grad()
-        ans_out, qst_out = self.model(image, question)
-        qst_loss = self.criterion(qst_out[:, :-1].flatten(end_dim=1), question[:, 1:].flatten())
-        loss = qst_loss if self.qst_only else self.criterion(ans_out, label) + qst_loss
+        loss = self.model._loss(image, question, label, self.qst_only)     # = CE(ans) + CE(qst[:, :-1]) of experiment.py:189-194
         loss.backward()
         if self.reducer is not None:
             self.reducer([p.grad for p in self._params if p.grad is not None])

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 import config
-from pcd_ops import linear_3xtf32
+from pcd_ops import linear_3xtf32, vocab_cross_entropy
 from pcdarts.model_search import Network
 
 
@@ -62,15 +62,24 @@ class QstEncoder(nn.Module):
         nn.init.xavier_uniform_(self.fc2.weight.data)
         nn.init.zeros_(self.fc2.bias)
 
-    def forward(self, question, image_embedding):
+    def forward(self, question, image_embedding, return_states=False):
         self.lstm.flatten_parameters()
         h0 = image_embedding.view(1, -1, self.hidden_size)
         words = self.tanh(self.word2vec(question)).transpose(0, 1)          # T x B x E (teacher forcing)
         out, (hidden, cell) = self.lstm(words, (h0, h0))
         feat = torch.cat((hidden, cell), 2).transpose(0, 1)
         feat = self.fc2(self.tanh(feat.reshape(feat.size(0), -1)))
+        states = self.tanh(out.transpose(0, 1))                              # B x T x H, input of the vocabulary projection
+        if return_states:
+            return feat, states
         # vocabulary projection (35 GFLOP at B=64): tcgen05 tensor cores, fp32-accurate 3xTF32 split
-        return feat, linear_3xtf32(self.tanh(out.transpose(0, 1)), self.fc1.weight, self.fc1.bias)
+        return feat, linear_3xtf32(states, self.fc1.weight, self.fc1.bias)
+
+    def next_word_loss(self, states, question):
+        """CE(fc1(states)[:, :-1], question[:, 1:]) (vqa_model.py:356-358), projection and loss fused: the last time step
+        is masked out instead of sliced away."""
+        targets = torch.cat((question[:, 1:], question.new_full((question.size(0), 1), -100)), dim=1)
+        return vocab_cross_entropy(states, self.fc1.weight, self.fc1.bias, targets)
 
     def sample(self, prob):
         if self.deterministic:
@@ -164,8 +173,11 @@ class VqaModel(VqaModelBase):
         return twin
 
     def _loss(self, images, questions, labels, qst_only=False):
-        ans_out, qst_out = self(images, questions)
-        qst_loss = self.criterion(qst_out[:, :-1].flatten(end_dim=1), questions[:, 1:].flatten())
+        """vqa_model.py:351-364; same value and gradients as CE on `self(images, questions)`, but the question logits stay
+        inside the fused projection + cross-entropy op."""
+        img_feature = self.img_encoder(images)
+        qst_feature, states = self.qst_encoder(questions, img_feature, return_states=True)
+        qst_loss = self.qst_encoder.next_word_loss(states, questions)
         if qst_only:
             return qst_loss
-        return self.criterion(ans_out, labels) + qst_loss
+        return self.criterion(self._answer(img_feature, qst_feature), labels) + qst_loss

@@ -83,6 +83,27 @@ def test_linear_3xtf32_vs_fp64(M, K, N):
         P.assert_close(got.double(), ref, 5e-5, name)
 
 
+# fused vocabulary projection + cross-entropy (ignored rows, padded pitch) vs an fp64 reference
+@pytest.mark.parametrize("B,T,K,V", [(64, 30, 512, 17858), (6, 30, 16, 41), (4, 5, 32, 1000)])
+def test_vocab_cross_entropy_vs_fp64(B, T, K, V):
+    import torch.nn.functional as F
+    from pcd_ops import vocab_cross_entropy
+    g = torch.Generator().manual_seed(B + T + K + V)
+    x = torch.randn(B, T, K, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(V, K, generator=g) / K ** 0.5).to(DEV).requires_grad_(True)
+    b = (0.1 * torch.randn(V, generator=g)).to(DEV).requires_grad_(True)
+    q = torch.randint(0, V, (B, T), generator=g).to(DEV)
+    tg = torch.cat((q[:, 1:], q.new_full((B, 1), -100)), 1)
+    loss = vocab_cross_entropy(x, w, b, tg)
+    (3.0 * loss).backward()
+    xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    ref = F.cross_entropy(F.linear(xr, wr, br)[:, :-1].flatten(end_dim=1), q[:, 1:].flatten())
+    (3.0 * ref).backward()
+    P.assert_close(loss.double(), ref, 1e-5, "loss")
+    for got, r, name in ((x.grad, xr.grad, "dx"), (w.grad, wr.grad, "dw"), (b.grad, br.grad, "db")):
+        P.assert_close(got.double(), r, 5e-5, name)
+
+
 def test_vqa_model_golden():
     P.vqa_case(DEV)
 
