@@ -165,6 +165,14 @@ static void fill_edge_bwd_args(EdgeBwdArgs& a, const EdgeGeom& q, const EdgeG* e
     }
 }
 
+// does this edge geometry run the v3 backward kernels (merged partial-grad slots)?  Pointer alignment is checked again
+// at launch; the arenas handed to the cell / MixedOp entry points are 16-byte aligned by contract.
+static bool edge_bwd_is_v3(const EdgeGeom& q) {
+    int thA = 0, thB = 0;
+    return q.Ws % 4 == 0 && q.Hs == q.S * q.Ho && q.Ws == q.S * q.Wo && bwd2_tile(q.c, q.S, q.Ho, q.Wo, &thA) &&
+           bwd2_tile(q.c, 1, q.Ho, q.Wo, &thB);
+}
+
 // v3 weight-gradient jobs for edges whose data jobs already ran (any number of edges, one stride)
 static int run_edge_wgrad2(const EdgeGeom& q, const EdgeG* edges, int n, float eps, void* stream) {
     int thA = 0;
@@ -184,17 +192,22 @@ static int run_edge_wgrad2(const EdgeGeom& q, const EdgeG* edges, int n, float e
 // gradients are either launched here (defer == nullptr) or left to the caller (*defer set to 1), which batches
 // them over the whole cell.  Other geometries run the generic v2 kernels (weight grads inline).
 static int run_edge_bwd(const EdgeGeom& q, const EdgeG* edges, int n, float eps, int need_wgrad, void* stream,
-                        int* defer = nullptr) {
+                        int* defer = nullptr, int* merged = nullptr) {
     if (defer) *defer = 0;
+    if (merged) *merged = 0;
     if (n == 0) return PCD_OK;
     if (n > kMaxEdgesPerLaunch) return PCD_ERR_ARG;
     EdgeBwdArgs a;
     bool al;
     fill_edge_bwd_args(a, q, edges, n, eps, need_wgrad, &al);
     int thA = 0, thB = 0;
-    if (al && q.Ws % 4 == 0 && bwd2_tile(q.c, q.S, q.Ho, q.Wo, &thA) && bwd2_tile(q.c, 1, q.Ho, q.Wo, &thB)) {
+    if (edge_bwd_is_v3(q)) {
+        if (!al) return PCD_ERR_ALIGN;
+        bwd2_tile(q.c, q.S, q.Ho, q.Wo, &thA);
+        bwd2_tile(q.c, 1, q.Ho, q.Wo, &thB);
         a.need_wgrad = 0;
         a.TH = thB; a.TW = q.Wo; a.tiles_x = 1;
+        if (merged) *merged = 1;         // edges[i].pd: two zeroed slots accumulated with reductions (caller's job)
         PCD_TRY(launch_bwdB2(a, q.c, n * 2, stream));
         a.TH = thA;
         PCD_TRY(launch_bwdA2(a, q.c, n * bwdA_njobs(q.S), stream));
@@ -260,6 +273,7 @@ struct CellLayout {
     int node_of[PCD_MAX_EDGES], src_of[PCD_MAX_EDGES], stride[PCD_MAX_EDGES], first_edge[PCD_MAX_STEPS];
     long long par[PCD_MAX_EDGES], run[PCD_MAX_EDGES], nbt[PCD_MAX_EDGES], stats[PCD_MAX_EDGES], bstats[PCD_MAX_EDGES];
     long long saved[PCD_MAX_EDGES], ga[PCD_MAX_EDGES], dxs[PCD_MAX_EDGES];
+    long long pd2[PCD_MAX_EDGES], pd2_begin, pd2_floats;     // v3: two merged partial-grad slots per edge, contiguous over the cell
     long long pre_par[2], pre_run[2], pre_nbt[2], pre_stats[2], pre_bstats[2], pre_out[2], pre_dout[2];
     long long dn[PCD_MAX_STEPS];
     pcd_cell_sizes tot;
@@ -310,6 +324,12 @@ static int cell_layout(const pcd_cell_shape& s, CellLayout& L) {
     }
     const long long node = (long long)L.B * L.C * L.Ho * L.Wo;
     for (int i = 0; i < 3; ++i) { L.dn[i] = wk; wk += node; }
+    L.pd2_begin = wk;
+    for (int k = 0; k < PCD_MAX_EDGES; ++k) {
+        const long long in_px = (long long)L.B * c * (L.stride[k] == 2 ? L.Hs * L.Ws : L.Ho * L.Wo);
+        L.pd2[k] = wk; wk += 2 * in_px;
+    }
+    L.pd2_floats = wk - L.pd2_begin;
     L.tot.param_floats = par; L.tot.running_floats = run; L.tot.nbt_int64 = nbt;
     L.tot.out_floats = 4 * node; L.tot.saved_floats = sv; L.tot.stats_doubles = st;
     L.tot.bwd_work_floats = wk; L.tot.bwd_stats_doubles = bst;
@@ -487,11 +507,13 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
     const long long node = (long long)L.B * L.C * L.Ho * L.Wo;
     PCD_TRY(zero_async(a->bstats, L.tot.bwd_stats_doubles * sizeof(double), stream));
     if (a->need_param_grads) PCD_TRY(zero_async(a->grad_params, L.tot.param_floats * sizeof(float), stream));
+    PCD_TRY(zero_async(a->work + L.pd2_begin, L.pd2_floats * sizeof(float), stream));      // merged partial-grad slots
     auto dn_ptr = [&](int i, long long& ns) -> const float* {
         if (i == 3) { ns = 4 * (node / L.B); return a->grad_out + 3 * (node / L.B); }
         ns = node / L.B;
         return a->work + L.dn[i];
     };
+    int edge_merged[PCD_MAX_EDGES] = {0};
     EdgeG wq[2][PCD_MAX_EDGES];          // edges whose weight-grad jobs are deferred, by stride
     EdgeGeom wgeo[2];
     int nwq[2] = {0, 0};
@@ -529,12 +551,16 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
             eg[n].alpha = a->weights + e * PCD_NUM_PRIMITIVES;
             eg[n].beta = a->weights2 + e;
             eg[n].ga = a->work + L.ga[e];
-            eg[n].pd = a->work + L.dxs[e];
             q.S = L.stride[e]; q.Hs = s.H; q.Ws = s.W;
+            eg[n].pd = a->work + (edge_bwd_is_v3(q) ? L.pd2[e] : L.dxs[e]);
             ++n;
         }
-        int deferred = 0;
-        PCD_TRY(run_edge_bwd(q, eg, n, eps, a->need_param_grads, stream, &deferred));
+        int deferred = 0, merged = 0;
+        PCD_TRY(run_edge_bwd(q, eg, n, eps, a->need_param_grads, stream, &deferred, &merged));
+        for (int e = 0; e < PCD_MAX_EDGES; ++e) {
+            const int j = L.src_of[e];
+            if (!((i == 0) ? (j >= 2) : (j != i + 1))) edge_merged[e] = merged;
+        }
         if (deferred && n > 0) {
             const int g = q.S - 1;
             wgeo[g] = q;
@@ -559,8 +585,8 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
                 if (m >= kMaxSrcEdges) return PCD_ERR_ARG;
                 long long cns;
                 const float* cdn = dn_ptr(L.node_of[e], cns);
-                sg.e[m].pd = a->work + L.dxs[e]; sg.e[m].dn = cdn; sg.e[m].dn_ns = cns;
-                sg.e[m].beta = a->weights2 + e; sg.e[m].stride = L.stride[e];
+                sg.e[m].pd = a->work + (edge_merged[e] ? L.pd2[e] : L.dxs[e]); sg.e[m].dn = cdn; sg.e[m].dn_ns = cns;
+                sg.e[m].beta = a->weights2 + e; sg.e[m].stride = L.stride[e]; sg.e[m].merged = edge_merged[e];
                 ++m;
             }
             sg.nedges = m;
@@ -670,12 +696,15 @@ int pcd_mixedop_backward(const pcd_mixedop_bwd_args* a, void* stream) {
     eg.x = a->x; eg.x_ns = es.x_ns; eg.dn = a->grad_out; eg.dn_ns = C * q.Ho * q.Wo; eg.saved = a->saved; eg.stats = a->stats;
     eg.bstats = a->bstats; eg.par = a->params; eg.gpar = a->need_param_grads ? a->grad_params : nullptr;
     eg.alpha = a->weights; eg.beta = nullptr; eg.ga = a->work; eg.pd = a->work + 2 * q.nslot();
-    PCD_TRY(run_edge_bwd(q, &eg, 1, a->shape.bn_eps, a->need_param_grads, stream));
+    int merged = 0;
+    if (edge_bwd_is_v3(q)) PCD_TRY(zero_async(eg.pd, (size_t)2 * q.B * q.c * q.Hs * q.Ws * sizeof(float), stream));
+    PCD_TRY(run_edge_bwd(q, &eg, 1, a->shape.bn_eps, a->need_param_grads, stream, nullptr, &merged));
     SourceGradArgs sg;
     memset(&sg, 0, sizeof sg);
     sg.B = q.B; sg.C = (int)C; sg.Hs = q.Hs; sg.Ws = q.Ws; sg.x = a->x; sg.x_ns = es.x_ns; sg.g0 = nullptr;
     sg.out = a->grad_x; sg.out_ns = es.x_ns; sg.nedges = 1;
     sg.e[0].pd = eg.pd; sg.e[0].dn = a->grad_out; sg.e[0].dn_ns = eg.dn_ns; sg.e[0].beta = nullptr; sg.e[0].stride = q.S;
+    sg.e[0].merged = merged;
     PCD_TRY(run_source_grad(sg, stream));
     ArchGradArgs ag;
     memset(&ag, 0, sizeof ag);

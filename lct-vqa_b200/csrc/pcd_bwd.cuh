@@ -154,6 +154,7 @@ struct SrcEdge {
     long long dn_ns;
     const float* beta;     // null => 1
     int stride;
+    int merged;            // 1: slot 0 = sum of the pre-mask partials (A3 A5 D3 D5 FR), slot 1 = max-pool + avg-pool(+identity)
 };
 
 constexpr int kMaxSrcEdges = 4;
@@ -190,6 +191,14 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int n) {
             for (int k = 0; k < a.nedges; ++k) {
                 const SrcEdge& e = a.e[k];
                 const float* pd = e.pd + ((long long)n * c + ch) * HW + p;
+                if (e.merged) {
+                    const F4 m = *reinterpret_cast<const F4*>(pd), q4 = *reinterpret_cast<const F4*>(pd + pslot);
+                    v.x += (xv.x > 0.f ? m.x : 0.f) + q4.x;
+                    v.y += (xv.y > 0.f ? m.y : 0.f) + q4.y;
+                    v.z += (xv.z > 0.f ? m.z : 0.f) + q4.z;
+                    v.w += (xv.w > 0.f ? m.w : 0.f) + q4.w;
+                    continue;
+                }
                 F4 m = {0.f, 0.f, 0.f, 0.f};
                 for (int s = 0; s < 4; ++s) {
                     const F4 t = *reinterpret_cast<const F4*>(pd + s * pslot);
@@ -258,6 +267,10 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int n) {
             const SrcEdge& e = a.e[k];
             if (ch < c) {
                 const float* pd = e.pd + ((long long)n * c + ch) * HW + p;
+                if (e.merged) {
+                    v += (xb[p] > 0.f ? pd[0] : 0.f) + pd[pslot];
+                    continue;
+                }
                 float m = pd[0] + pd[pslot] + pd[2 * pslot] + pd[3 * pslot];
                 if (e.stride == 2) m += pd[6 * pslot];
                 v += (xb[p] > 0.f ? m : 0.f) + pd[4 * pslot] + pd[5 * pslot];

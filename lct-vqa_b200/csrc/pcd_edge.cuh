@@ -125,6 +125,14 @@ PCD_HD void st4(float* p, float a, float b, float c, float d) {
     F4 t = {a, b, c, d};
     *reinterpret_cast<F4*>(p) = t;
 }
+// p[0..3] += (a, b, c, d), no return value: one 16-byte reduction at the L2 (sm_90+)
+PCD_HD void red4(float* p, float a, float b, float c, float d) {
+#if PCD_CUDA
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+#else
+    p[0] += a; p[1] += b; p[2] += c; p[3] += d;
+#endif
+}
 
 // Tile rows that span the full image width W (the compile-time-tile kernels): dst[C][ROWS][W + 8] <- f(ch, src row),
 // image rows gy0 .. gy0 + ROWS - 1 (zero outside the image); the two 4-float column halos are zero padding.

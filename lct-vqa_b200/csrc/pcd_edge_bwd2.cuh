@@ -218,7 +218,10 @@ PCD_HD void bwdA2_conv_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
     PCD_SYNC();
     dt_rows<C, RH, TW, IW, 4>(DT, DZ, WT, g.oy0 - HY, a.Ho);
     PCD_SYNC();
-    float* pd_img = e.pd + (long long)slot * a.B * C * a.Hs * a.Ws + (long long)g.n * C * a.Hs * a.Ws;
+    // v3 layout of the partial input grads: slot 0 accumulates every pre-mask partial (A3 A5 D3 D5 FR), slot 1 the two
+    // pool partials; both are zeroed by the launcher and summed with 16-byte reductions (SrcEdge::merged)
+    (void)slot;
+    float* pd_img = e.pd + (long long)g.n * C * a.Hs * a.Ws;
     constexpr int AH = S * TH, AW = S * TW, APW4 = AW / 4, ANP = (AH / 4) * APW4;
     for_tasks_rolled<C * ANP>([&](int task) {
         const int ch = task / ANP, patch = task - ch * ANP;
@@ -234,7 +237,7 @@ PCD_HD void bwdA2_conv_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
             dw_bwd_data_s2<KS, DIL>(DT + ch * RH * IW, IW, HY, qy, qx, w_dw + ch * KS * KS, acc);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            st4(pd_img + ((long long)ch * a.Hs + S * g.oy0 + qy + i) * a.Ws + qx, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            red4(pd_img + ((long long)ch * a.Hs + S * g.oy0 + qy + i) * a.Ws + qx, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     });
 }
 
@@ -323,7 +326,7 @@ PCD_HD void bwdA2_pool_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
     PCD_SYNC();
     // gather over the windows that contain each input pixel
     constexpr int AH = S * TH, AW = S * TW, AW4 = AW / 4;
-    float* pd_img = e.pd + (long long)(4 + which) * a.B * C * a.Hs * a.Ws + (long long)g.n * C * a.Hs * a.Ws;
+    float* pd_img = e.pd + (long long)a.B * C * a.Hs * a.Ws + (long long)g.n * C * a.Hs * a.Ws;      // slot 1 (both pools)
     const float idc = beta * e.alpha[3];
     for_tasks_rolled<C * AH * AW4>([&](int task) {
         const int q4 = task % AW4, rr = task / AW4, qy = rr % AH, ch = rr / AH;
@@ -350,7 +353,7 @@ PCD_HD void bwdA2_pool_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
             const F4 h = ld4(dn_img + (long long)(4 * ch) * HW + (long long)gy * TW + gx);
             s[0] = fmaf(idc, h.x, s[0]); s[1] = fmaf(idc, h.y, s[1]); s[2] = fmaf(idc, h.z, s[2]); s[3] = fmaf(idc, h.w, s[3]);
         }
-        st4(pd_img + ((long long)ch * a.Hs + gy) * a.Ws + gx, s[0], s[1], s[2], s[3]);
+        red4(pd_img + ((long long)ch * a.Hs + gy) * a.Ws + gx, s[0], s[1], s[2], s[3]);
     });
 }
 
@@ -371,7 +374,7 @@ PCD_HD void bwdA2_fr_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, flo
     PCD_SYNC();
     const float* dn_img = e.dn + (long long)g.n * e.dn_ns;
     const float* F = e.saved + slot_f() * nslot + (long long)g.n * C * HW;
-    float* pd_img = e.pd + 6LL * a.B * C * a.Hs * a.Ws + (long long)g.n * C * a.Hs * a.Ws;
+    float* pd_img = e.pd + (long long)g.n * C * a.Hs * a.Ws;      // slot 0 (pre-mask partials)
     // task = (strip of 4 output pixels, group of 4 input channels)
     for_tasks_rolled<(NPIX / 4) * (C / 4)>([&](int task) {
         const int st = task % (NPIX / 4), cig = task / (NPIX / 4);
@@ -407,10 +410,10 @@ PCD_HD void bwdA2_fr_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, flo
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float* p0 = pd_img + ((long long)(cig * 4 + q) * a.Hs + 2 * oy) * a.Ws + 2 * ox;
-            st4(p0, r0[q][0], 0.f, r0[q][1], 0.f);
-            st4(p0 + 4, r0[q][2], 0.f, r0[q][3], 0.f);
-            st4(p0 + a.Ws, 0.f, r1[q][0], 0.f, r1[q][1]);
-            st4(p0 + a.Ws + 4, 0.f, r1[q][2], 0.f, r1[q][3]);
+            red4(p0, r0[q][0], 0.f, r0[q][1], 0.f);
+            red4(p0 + 4, r0[q][2], 0.f, r0[q][3], 0.f);
+            red4(p0 + a.Ws, 0.f, r1[q][0], 0.f, r1[q][1]);
+            red4(p0 + a.Ws + 4, 0.f, r1[q][2], 0.f, r1[q][3]);
         }
     });
 }
