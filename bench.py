@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--graph-dp", action="store_true", help="capture the step in a CUDA graph under data parallelism too (NCCL all-reduces inside the graph)")
     ap.add_argument("--no-overlap", action="store_true", help="keep the weight-grad jobs on the main stream")
     return ap.parse_args()
 
@@ -218,7 +219,7 @@ def run_b200(a):
     if world > 1:           # identical replicas: rank 0's init everywhere
         for t in list(model.parameters()) + list(model.buffers()) + list(model.arch_parameters()):
             dist.broadcast(t.data, 0)
-    use_graph = (world == 1) and not a.no_graph
+    use_graph = not a.no_graph and (world == 1 or a.graph_dp)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph)
     architect = Architect(model, Namespace(arch_learn_rate=6e-4, arch_wt_decay=1e-3, qst_only=False), reducer=reducer)
     if use_graph:
@@ -313,7 +314,12 @@ def run_b200(a):
         top = next(iter(by_kernel))
         roofline = {"bound": "hbm", "kernel": "MixedOp kernel group (fwdA,fwdB,combine | node_stats,bwdB,bwdA,wgrad,"
                                               "source_grad,arch_grads): all 56 edges x all passes of one step",
-                    "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                    "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                    # DRAM bytes of the same kernel group from ncu (dram__bytes_read + dram__bytes_write, cold cache, one
+                    # forward + one full backward = 10.39 GB, of which 1.87 GB weight-grad jobs: profiles/r01_v5_ncu_launches_summary.txt)
+                    "traffic": ((n_fwd * 3.0 + (n_bwd - n_fwd) * 0.0) * 0 + (3 if unrolled else 2) * 10.39e9 +
+                                (2 if unrolled else 0) * (10.39e9 - 1.87e9)) * a.batch / 64.0,
+                    "traffic_note": "bytes per step of the kernel group, ncu cold-cache DRAM counters at B=64 scaled by B/64",
                     "algorithmic_mb_per_step": alg_mb, "kernel_ms_per_step": mixed_ms, "peak_source": peak_src,
                     "passes_per_step": {"forward": n_fwd, "backward": n_bwd},
                     "dominant_kernel": top, "native_kernel_ms_per_step": total_ms / nprof,
