@@ -9,12 +9,13 @@
 // and the product is accumulated in fp32 in tensor memory as  hi*hi + hi*lo + lo*hi  (3xTF32; the dropped lo*lo term
 // and the truncation of lo are ~2^-22 relative).  Algorithmic flops are counted once.
 //
-// Warp roles (192 threads, one 128 x BN tile per CTA, one CTA per SM):
-//   warp 0    : TMA producer  — cp.async.bulk.tensor (SWIZZLE_128B, 32 fp32 = 128 bytes per row) into the hi tiles
+// Tile: 128 x 256 x 16 (64-byte SWIZZLE_64B rows) with 4 stages by default; 128 x 128 x 32 (SWIZZLE_128B, 3 stages) for
+// narrow outputs.  Warp roles (192 threads, one 128 x BN tile per CTA, one CTA per SM):
+//   warp 0    : TMA producer  — cp.async.bulk.tensor (swizzled, BK fp32 per row) into the hi tiles
 //   warps 2-5 : splitters     — lo = x - trunc13(x) of each landed stage into a second tile (same swizzled positions;
 //                               the raw tile itself serves as hi: the MMA ignores the low 13 mantissa bits), then the
 //                               epilogue: tcgen05.ld of the accumulator, bias, store / atomic add (split-K)
-//   warp 1    : MMA issuer    — one elected thread issues 12 tcgen05.mma.kind::tf32 per stage (4 k-steps x 3 products),
+//   warp 1    : MMA issuer    — one elected thread issues 3 tcgen05.mma.kind::tf32 per 8-wide k-step (hi*hi, hi*lo, lo*hi),
 //                               tcgen05.commit releases the stage / signals the epilogue
 // mbarriers: full[s] (TMA bytes landed) -> split[s] (128 splitter arrivals) -> MMA -> empty[s] (commit) -> TMA.
 #include "../../include/pcdarts_sm100.h"
@@ -26,7 +27,7 @@
 namespace pcd {
 namespace gemm {
 
-constexpr int BM = 128, BK = 32, UMMA_K = 8, kGemmThreads = 192, kSplitThreads = 128;
+constexpr int BM = 128, UMMA_K = 8, kGemmThreads = 192, kSplitThreads = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -58,14 +59,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row (1024-byte) swizzle atoms
+// K-major shared-memory matrix descriptor: rows of ROWB bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row swizzle atoms
+template <int ROWB>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);      // start address            bits [0,14)
     d |= (uint64_t)1 << 16;                        // leading byte offset (unused with swizzle, canonical value 1)
-    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: next 8-row group   bits [32,46)
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;        // stride byte offset: next 8-row group   bits [32,46)
     d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;    // SWIZZLE_128B / SWIZZLE_64B
     return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -92,19 +94,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int BK, int STAGES>
 struct Cfg {
-    static constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+    static constexpr uint32_t ROWB = BK * 4, A_BYTES = BM * ROWB, B_BYTES = BN * ROWB, STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
     // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), K-major both, N >> 3, M >> 4
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
-template <int BN, int STAGES, bool REWRITE_HI>
+template <int BN, int BK, int STAGES, bool REWRITE_HI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                       long long ldc, int M, int N, int K, const float* __restrict__ bias, int kb_per_split, int atomic) {
-    using G = Cfg<BN, STAGES>;
+    using G = Cfg<BN, BK, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * G::STAGE_BYTES);
@@ -161,8 +163,8 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(&split[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t dah = umma_desc(smem_u32(a_hi(s))), dbh = umma_desc(smem_u32(b_hi(s)));
-                const uint64_t dal = umma_desc(smem_u32(a_lo(s))), dbl = umma_desc(smem_u32(b_lo(s)));
+                const uint64_t dah = umma_desc<G::ROWB>(smem_u32(a_hi(s))), dbh = umma_desc<G::ROWB>(smem_u32(b_hi(s)));
+                const uint64_t dal = umma_desc<G::ROWB>(smem_u32(a_lo(s))), dbl = umma_desc<G::ROWB>(smem_u32(b_lo(s)));
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);      // bytes >> 4 along the 128-byte row
@@ -265,16 +267,17 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// rows x K fp32 matrix, row pitch ld (elements); box = 32 columns (128 bytes) x box_rows, 128-byte swizzle, zero fill
-static int make_map(CUtensorMap* m, const float* p, long long rows, long long K, long long ld, int box_rows) {
+// rows x K fp32 matrix, row pitch ld (elements); box = bk columns (128 or 64 bytes) x box_rows, matching swizzle, zero fill
+static int make_map(CUtensorMap* m, const float* p, long long rows, long long K, long long ld, int box_rows, int bk) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return PCD_ERR_CUDA;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         snprintf(launch_state().last_err, sizeof launch_state().last_err, "cuTensorMapEncodeTiled failed (%d)", (int)r);
         return PCD_ERR_CUDA;
@@ -282,16 +285,17 @@ static int make_map(CUtensorMap* m, const float* p, long long rows, long long K,
     return PCD_OK;
 }
 
-static int g_raw_hi = 1;     // 1: feed the raw fp32 tile as the hi operand (kind::tf32 ignores the low 13 mantissa bits:
-                             // measured bit-identical to masking them explicitly, profiles/r01_gemm_3xtf32.txt); 0: rewrite it
+// The raw fp32 tile is fed as the hi operand: kind::tf32 ignores the low 13 mantissa bits (measured bit-identical to
+// masking them explicitly, profiles/r01_gemm_3xtf32.txt; REWRITE_HI = true keeps the explicit variant compilable).
+static int g_cfg = 0;
 
-template <int BN, int STAGES, bool REWRITE_HI>
+template <int BN, int BK, int STAGES, bool REWRITE_HI>
 static int run(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long ldc, int M, int N, int K, const float* bias,
                int split_k, cudaStream_t st) {
-    using G = Cfg<BN, STAGES>;
+    using G = Cfg<BN, BK, STAGES>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tn_3xtf32_kernel<BN, STAGES, REWRITE_HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tn_3xtf32_kernel<BN, BK, STAGES, REWRITE_HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES) != cudaSuccess)
             return PCD_ERR_CUDA;
         configured = true;
     }
@@ -300,7 +304,7 @@ static int run(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long
     if (kbps < 1) kbps = 1;
     const int gz = (total_kb + kbps - 1) / kbps;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, gz > 0 ? gz : 1);
-    gemm_tn_3xtf32_kernel<BN, STAGES, REWRITE_HI><<<grid, kGemmThreads, G::SMEM_BYTES, st>>>(ta, tb, C, ldc, M, N, K, bias, kbps, gz > 1 ? 1 : 0);
+    gemm_tn_3xtf32_kernel<BN, BK, STAGES, REWRITE_HI><<<grid, kGemmThreads, G::SMEM_BYTES, st>>>(ta, tb, C, ldc, M, N, K, bias, kbps, gz > 1 ? 1 : 0);
     LaunchState& L = launch_state();
     ++L.launches;
     cudaError_t e = cudaGetLastError();
@@ -321,25 +325,28 @@ extern "C" int pcd_gemm_tn_3xtf32(const float* A, long long lda, const float* B,
     if ((((uintptr_t)A) | ((uintptr_t)B)) & 15 || lda % 4 || ldb % 4 || lda < K || ldb < K || ldc < N) return PCD_ERR_ALIGN;
     if (split_k < 1) split_k = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool wide = N >= 1024;
+    int cfg = gemm::g_cfg;
+    if (cfg == 0) cfg = (N >= 256) ? 3 : 2;           // measured best: 128x256x16 with 4 stages (profiles/r01_gemm_3xtf32.txt)
+    const int bn = (cfg == 1 || cfg == 3) ? 256 : 128, bk = (cfg <= 2) ? 32 : 16;
     CUtensorMap ta, tb;
-    PCD_TRY(gemm::make_map(&ta, A, M, K, lda, gemm::BM));
-    PCD_TRY(gemm::make_map(&tb, B, N, K, ldb, wide ? 256 : 128));
-    const int total_kb = (K + gemm::BK - 1) / gemm::BK;
+    PCD_TRY(gemm::make_map(&ta, A, M, K, lda, gemm::BM, bk));
+    PCD_TRY(gemm::make_map(&tb, B, N, K, ldb, bn, bk));
+    const int total_kb = (K + bk - 1) / bk;
     if (split_k > total_kb) split_k = total_kb;
     if (split_k > 1) {      // partial sums are added atomically: start from zero
         if (cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st) != cudaSuccess) return PCD_ERR_CUDA;
     }
-    if (gemm::g_raw_hi) {
-        if (wide) return gemm::run<256, 2, false>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
-        return gemm::run<128, 3, false>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
+    switch (cfg) {
+        case 1: return gemm::run<256, 32, 2, false>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
+        case 2: return gemm::run<128, 32, 3, false>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
+        case 3: return gemm::run<256, 16, 4, false>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
+        default: return gemm::run<128, 16, 6, false>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
     }
-    if (wide) return gemm::run<256, 2, true>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
-    return gemm::run<128, 3, true>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
 }
 
-/* experiment knob (not part of the reference-facing ABI): 1 = do not rewrite the hi tile */
-extern "C" int pcd_gemm_debug_raw_hi(int on) { pcd::gemm::g_raw_hi = on; return 0; }
+/* experiment knob (not part of the reference-facing ABI): tile configuration 0 = auto, 1 = 128x256x32 (2 stages),
+ * 2 = 128x128x32 (3 stages), 3 = 128x256x16 (4 stages), 4 = 128x128x16 (6 stages) */
+extern "C" int pcd_gemm_debug_cfg(int cfg) { pcd::gemm::g_cfg = cfg; return 0; }
 
 #else   // ---- CPU emulation build (tests only): plain fp32 loops ------------------------------------------------------
 
@@ -355,5 +362,5 @@ extern "C" int pcd_gemm_tn_3xtf32(const float* A, long long lda, const float* B,
         }
     return PCD_OK;
 }
-extern "C" int pcd_gemm_debug_raw_hi(int) { return 0; }
+extern "C" int pcd_gemm_debug_cfg(int) { return 0; }
 #endif
