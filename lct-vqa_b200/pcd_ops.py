@@ -492,11 +492,18 @@ def _gemm_tn(lib, a, lda, b, ldb, c, ldc, m, n, k, bias, split_k, ref):
                                         N.stream_for(ref)), "pcd_gemm_tn_3xtf32")
 
 
-class Linear3xTF32Function(torch.autograd.Function):
-    """y = x @ W^T + b through pcd_gemm_tn_3xtf32 (vqa_model.py:192-194 `fc1`, the vocabulary projection).
+def _auto_split(m, n, k):
+    """Split K over blockIdx.z when the output has too few 128 x 256 tiles to fill 148 SMs (keeps >= 8 k-blocks per split)."""
+    tiles = ((m + 127) // 128) * ((n + 255) // 256)
+    return max(1, min(32, (k // 16) // 8, (148 + tiles - 1) // tiles))
 
-    The TMA descriptors need 16-byte row pitches: the logits, their gradient and W^T live in buffers whose row pitch
-    is the vocabulary size rounded up to a multiple of 4 (pad columns are zero); y is returned as a view of it.
+
+class Linear3xTF32Function(torch.autograd.Function):
+    """y = x @ W^T + b through pcd_gemm_tn_3xtf32 (nn.Linear drop-in; the vocabulary projection vqa_model.py:192-194, the
+    image `fc` vqa_model.py:56,61, the question `fc2` and the answer head vqa_model.py:308-316).
+
+    The TMA descriptors need 16-byte row pitches: y, its gradient and the transposed operands of the backward products
+    live in buffers whose row pitch is rounded up to a multiple of 4 (pad columns are zero); y is returned as a view.
     """
 
     @staticmethod
@@ -508,7 +515,7 @@ class Linear3xTF32Function(torch.autograd.Function):
         n = w.shape[0]
         npad = _pad4(n)
         out = _empty((m, npad), torch.float32, x2.device)
-        _gemm_tn(lib, x2, k, w, k, out, npad, m, n, k, _f32c(bias) if bias is not None else None, 1, x2)
+        _gemm_tn(lib, x2, k, w, k, out, npad, m, n, k, _f32c(bias) if bias is not None else None, _auto_split(m, n, k), x2)
         ctx.save_for_backward(x2, w)
         ctx.meta = (x.shape, n, npad, bias is not None)
         return out[:, :n].view(*x.shape[:-1], n)
@@ -519,36 +526,34 @@ class Linear3xTF32Function(torch.autograd.Function):
         xshape, n, npad, has_bias = ctx.meta
         lib = N.lib_for(x2)
         m, k = x2.shape
-        g2 = gy.reshape(m, n)
+        g2 = _f32c(gy.reshape(m, n))
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gp = _empty((m, npad), torch.float32, x2.device)        # dL/dy with a 16-byte row pitch
-            gp[:, :n].copy_(g2)
-            if npad != n:
+            if npad == n:
+                gp = g2
+            else:
+                gp = _empty((m, npad), torch.float32, x2.device)    # dL/dy with a 16-byte row pitch
+                gp[:, :n].copy_(g2)
                 gp[:, n:].zero_()
-            wt = _empty((k, npad), torch.float32, x2.device)        # W^T, same pitch
-            wt[:, :n].copy_(w.t())
-            if npad != n:
-                wt[:, n:].zero_()
+            wt = _transpose_pad(lib, w, k, n, k, npad, x2)          # W^T (k, npad)
             gx2 = _empty((m, k), torch.float32, x2.device)
-            split = max(1, min(32, npad // 1024))                   # long contraction: split K (also shortens the fp32 chains)
-            _gemm_tn(lib, gp, npad, wt, npad, gx2, k, m, k, npad, None, split, x2)
+            _gemm_tn(lib, gp, npad, wt, npad, gx2, k, m, k, npad, None, _auto_split(m, k, npad), x2)
             gx = gx2.view(xshape)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
-            gt = g2.t().contiguous()                                # (n, m)
+            mp = _pad4(m)
+            gt = _transpose_pad(lib, g2, n, m, n, mp, x2)           # (n, mp)
             if has_bias and ctx.needs_input_grad[2]:
                 gb = gt.sum(1)
             if ctx.needs_input_grad[1]:
-                xt = x2.t().contiguous()                            # (k, m)
+                xt = _transpose_pad(lib, x2, k, m, k, mp, x2)       # (k, mp)
                 gw = _empty((n, k), torch.float32, x2.device)
-                _gemm_tn(lib, gt, m, xt, m, gw, k, n, k, m, None, 1, x2)
+                _gemm_tn(lib, gt, mp, xt, mp, gw, k, n, k, mp, None, _auto_split(n, k, mp), x2)
         return gx, gw, gb
 
 
 def linear_3xtf32(x, weight, bias):
     """nn.Linear forward on the tensor cores when the shapes allow TMA (rows and depth multiples of 4), else F.linear."""
-    m = x.numel() // x.shape[-1]
-    if x.shape[-1] % 4 or m % 4 or not (x.is_cuda or N._emu_lib is not None):
+    if x.shape[-1] % 4 or not (x.is_cuda or N._emu_lib is not None):
         return torch.nn.functional.linear(x, weight, bias)
     return Linear3xTF32Function.apply(x, weight, bias)
 
@@ -599,7 +604,7 @@ class VocabCrossEntropyFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = _transpose_pad(lib, w, k, v, k, vp, x2)                     # W^T (k, vp)
             gx2 = _empty((m, k), torch.float32, x2.device)
-            _gemm_tn(lib, dl, vp, wt, vp, gx2, k, m, k, vp, None, max(1, min(32, vp // 1024)), x2)
+            _gemm_tn(lib, dl, vp, wt, vp, gx2, k, m, k, vp, None, max(_auto_split(m, k, vp), min(32, vp // 1024)), x2)
             gx = gx2.view(xshape)
         need_b = has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1] or need_b:

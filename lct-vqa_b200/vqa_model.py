@@ -28,7 +28,7 @@ class DartsEncoder(nn.Module):
         self.fc = nn.Linear(self.darts.output_ch * self.darts.output_size ** 2, embed_size)
 
     def forward(self, image):
-        feat = self.fc(self.darts(image))
+        feat = linear_3xtf32(self.darts(image), self.fc.weight, self.fc.bias)      # 12544 -> 512 on the tensor cores (split-K)
         return feat.div(feat.norm(p=2, dim=1, keepdim=True).detach())
 
 
@@ -68,7 +68,7 @@ class QstEncoder(nn.Module):
         words = self.tanh(self.word2vec(question)).transpose(0, 1)          # T x B x E (teacher forcing)
         out, (hidden, cell) = self.lstm(words, (h0, h0))
         feat = torch.cat((hidden, cell), 2).transpose(0, 1)
-        feat = self.fc2(self.tanh(feat.reshape(feat.size(0), -1)))
+        feat = linear_3xtf32(self.tanh(feat.reshape(feat.size(0), -1)), self.fc2.weight, self.fc2.bias)
         states = self.tanh(out.transpose(0, 1))                              # B x T x H, input of the vocabulary projection
         if return_states:
             return feat, states
@@ -151,8 +151,8 @@ class VqaModel(VqaModelBase):
 
     def _answer(self, img_feature, qst_feature):
         z = self.dropout(self.tanh(torch.mul(img_feature, qst_feature)))
-        z = self.dropout(self.tanh(self.fc1(z)))
-        return self.fc2(z)
+        z = self.dropout(self.tanh(linear_3xtf32(z, self.fc1.weight, self.fc1.bias)))
+        return linear_3xtf32(z, self.fc2.weight, self.fc2.bias)
 
     def forward(self, img, qst):
         img_feature = self.img_encoder(img)

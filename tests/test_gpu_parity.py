@@ -65,15 +65,17 @@ def test_w_step_with_wgrad_overlap_matches_golden():
 
 
 # tcgen05 3xTF32 projection (nn.Linear drop-in) vs an fp64 reference: forward, dX (split-K), dW, db; ragged tiles
-@pytest.mark.parametrize("M,K,N", [(1920, 512, 17858), (64, 512, 1000), (120, 36, 70), (256, 1024, 512)])
+@pytest.mark.parametrize("M,K,N", [(1920, 512, 17858), (64, 512, 1000), (120, 36, 70), (256, 1024, 512), (64, 12544, 512),
+                                   (64, 1000, 1000), (6, 16, 12)])
 def test_linear_3xtf32_vs_fp64(M, K, N):
     import torch.nn.functional as F
     from pcd_ops import linear_3xtf32
     g = torch.Generator().manual_seed(M + K + N)
-    x = torch.randn(M // 4, 4, K, generator=g).to(DEV).requires_grad_(True)
+    L = 4 if M % 4 == 0 else 2
+    x = torch.randn(M // L, L, K, generator=g).to(DEV).requires_grad_(True)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).requires_grad_(True)
     b = torch.randn(N, generator=g).to(DEV).requires_grad_(True)
-    G = torch.randn(M // 4, 4, N, generator=g).to(DEV)
+    G = torch.randn(M // L, L, N, generator=g).to(DEV)
     y = linear_3xtf32(x, w, b)
     (y * G).sum().backward()
     xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
