@@ -286,6 +286,21 @@ int pcd_ce_backward(const float* logits, long long ld, int M, int V, const long 
                     const float* scale, float* dlogits, void* stream);
 int pcd_transpose_pad(const float* src, long long ld_s, int R, int C, float* dst, long long ld_d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Single-layer LSTM recurrence of the question encoder (darts_vqa/vqa_model.py:165,176-184: nn.LSTM(300, 512, 1), T = 30,
+ * h0 = c0 = image embedding) as persistent cooperative kernels (one grid barrier per time step).  PyTorch gate order
+ * i, f, g, o.  gx = x W_ih^T + b_ih + b_hh ([T][B][4H], from pcd_gemm_tn_3xtf32).  Forward saves the gate activations
+ * `act`, the cell states `cs` and the outputs `hs`; backward turns (dhs, dhT, dcT) into dgates ([T][B][4H]; the weight /
+ * input gradients are GEMMs over it), dh0 and dc0.  B <= 64, H a power of two in [16, 512].  pbuf: scratch of
+ * pcd_lstm_pbuf_floats(B, H) floats.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pcd_lstm_pbuf_floats(int B, int H);
+int pcd_lstm_forward(int T, int B, int H, const float* gx, const float* w_hh, const float* h0, const float* c0,
+                     float* act, float* cs, float* hs, void* stream);
+int pcd_lstm_backward(int T, int B, int H, const float* dhs, const float* dhT, const float* dcT, const float* act,
+                      const float* cs, const float* c0, const float* w_hh, float* dgates, float* dh0, float* dc0,
+                      float* pbuf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

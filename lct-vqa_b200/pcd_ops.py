@@ -625,3 +625,85 @@ def vocab_cross_entropy(x, weight, bias, targets):
         logits = torch.nn.functional.linear(x, weight, bias)
         return torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), targets.reshape(-1), ignore_index=-100)
     return VocabCrossEntropyFunction.apply(x, weight, bias, targets)
+
+
+# --------------------------------------------------------------------------------------------
+# single-layer LSTM: dense projections on tcgen05, recurrence in persistent cooperative kernels
+# --------------------------------------------------------------------------------------------
+class LstmFunction(torch.autograd.Function):
+    """nn.LSTM(E, H, 1) forward/backward (time-major input (T, B, E), h0 = c0 given) — vqa_model.py:165,176-184.
+
+    gx = x W_ih^T + (b_ih + b_hh) and the four backward products (dx, dW_ih, dW_hh over all T*B rows) go through
+    pcd_gemm_tn_3xtf32; the two recurrences through pcd_lstm_forward / pcd_lstm_backward."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, w_ih, w_hh, b_ih, b_hh):
+        lib = N.lib_for(x)
+        xc, h0c, c0c, wi, wh = _f32c(x), _f32c(h0), _f32c(c0), _f32c(w_ih), _f32c(w_hh)
+        T, B, E = xc.shape
+        H = wh.shape[1]
+        dev = xc.device
+        x2 = xc.view(T * B, E)
+        gx = _empty((T * B, 4 * H), torch.float32, dev)
+        _gemm_tn(lib, x2, E, wi, E, gx, 4 * H, T * B, 4 * H, E, (b_ih + b_hh).detach().contiguous(), _auto_split(T * B, 4 * H, E), xc)
+        act = _empty((T, B, 4 * H), torch.float32, dev)
+        cs = _empty((T, B, H), torch.float32, dev)
+        hs = _empty((T, B, H), torch.float32, dev)
+        N.check(lib, lib.pcd_lstm_forward(T, B, H, N.ptr(gx), N.ptr(wh), N.ptr(h0c), N.ptr(c0c), N.ptr(act), N.ptr(cs), N.ptr(hs),
+                                          N.stream_for(xc)), "pcd_lstm_forward")
+        ctx.save_for_backward(xc, h0c, c0c, wi, wh, act, cs, hs)
+        return hs, hs[T - 1].clone(), cs[T - 1].clone()
+
+    @staticmethod
+    def backward(ctx, dhs, dhT, dcT):
+        xc, h0c, c0c, wi, wh, act, cs, hs = ctx.saved_tensors
+        lib = N.lib_for(xc)
+        T, B, E = xc.shape
+        H = wh.shape[1]
+        dev = xc.device
+        dhs = _f32c(dhs) if dhs is not None else None
+        dhT = _f32c(dhT) if dhT is not None else None
+        dcT = _f32c(dcT) if dcT is not None else None
+        dg = _empty((T * B, 4 * H), torch.float32, dev)
+        dh0 = _empty((B, H), torch.float32, dev)
+        dc0 = _empty((B, H), torch.float32, dev)
+        pbuf = _empty(lib.pcd_lstm_pbuf_floats(B, H), torch.float32, dev)
+        N.check(lib, lib.pcd_lstm_backward(T, B, H, N.ptr(dhs), N.ptr(dhT), N.ptr(dcT), N.ptr(act), N.ptr(cs), N.ptr(c0c), N.ptr(wh),
+                                           N.ptr(dg), N.ptr(dh0), N.ptr(dc0), N.ptr(pbuf), N.stream_for(xc)), "pcd_lstm_backward")
+        m = T * B
+        gx_in = gwi = gwh = gb = None
+        if ctx.needs_input_grad[0]:
+            wit = _transpose_pad(lib, wi, E, 4 * H, E, 4 * H, xc)              # W_ih^T (E, 4H)
+            gx_in = _empty((m, E), torch.float32, dev)
+            _gemm_tn(lib, dg, 4 * H, wit, 4 * H, gx_in, E, m, E, 4 * H, None, _auto_split(m, E, 4 * H), xc)
+            gx_in = gx_in.view(T, B, E)
+        if any(ctx.needs_input_grad[3:]):
+            mp = _pad4(m)
+            dgt = _transpose_pad(lib, dg, 4 * H, m, 4 * H, mp, xc)             # dgates^T (4H, mp)
+            gb = dgt.sum(1) if (ctx.needs_input_grad[5] or ctx.needs_input_grad[6]) else None
+            if ctx.needs_input_grad[3]:
+                xt = _transpose_pad(lib, xc.view(m, E), E, m, E, mp, xc)       # x^T (E, mp)
+                gwi = _empty((4 * H, E), torch.float32, dev)
+                _gemm_tn(lib, dgt, mp, xt, mp, gwi, E, 4 * H, E, mp, None, _auto_split(4 * H, E, mp), xc)
+            if ctx.needs_input_grad[4]:
+                hprev = torch.cat((h0c.unsqueeze(0), hs[:-1]), 0).view(m, H)   # h_{t-1} for every step
+                ht = _transpose_pad(lib, hprev, H, m, H, mp, xc)               # (H, mp)
+                gwh = _empty((4 * H, H), torch.float32, dev)
+                _gemm_tn(lib, dgt, mp, ht, mp, gwh, H, 4 * H, H, mp, None, _auto_split(4 * H, H, mp), xc)
+        return (gx_in, dh0 if ctx.needs_input_grad[1] else None, dc0 if ctx.needs_input_grad[2] else None, gwi, gwh,
+                gb if ctx.needs_input_grad[5] else None, gb if ctx.needs_input_grad[6] else None)
+
+
+def lstm_supported(x, hidden):
+    """Shapes the cooperative recurrence kernels take: batch <= 64, hidden a power of two in [16, 512], E % 4 == 0."""
+    return (x.is_cuda or N._emu_lib is not None) and x.dim() == 3 and x.shape[1] <= 64 and x.shape[2] % 4 == 0 and \
+        16 <= hidden <= 512 and (hidden & (hidden - 1)) == 0
+
+
+def lstm_forward(lstm, x, h0, c0):
+    """nn.LSTM(x, (h0, c0)) for a single-layer unidirectional module, through the native path when the shape allows."""
+    if lstm.num_layers != 1 or lstm.bidirectional or lstm.batch_first or not lstm_supported(x, lstm.hidden_size):
+        out, (h, c) = lstm(x, (h0, c0))
+        return out, (h, c)
+    out, hT, cT = LstmFunction.apply(x, h0[0], c0[0], lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)
+    return out, (hT.unsqueeze(0), cT.unsqueeze(0))

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 import config
-from pcd_ops import linear_3xtf32, vocab_cross_entropy
+from pcd_ops import linear_3xtf32, lstm_forward, vocab_cross_entropy
 from pcdarts.model_search import Network
 
 
@@ -66,7 +66,7 @@ class QstEncoder(nn.Module):
         self.lstm.flatten_parameters()
         h0 = image_embedding.view(1, -1, self.hidden_size)
         words = self.tanh(self.word2vec(question)).transpose(0, 1)          # T x B x E (teacher forcing)
-        out, (hidden, cell) = self.lstm(words, (h0, h0))
+        out, (hidden, cell) = lstm_forward(self.lstm, words, h0, h0)      # persistent recurrence kernels + tcgen05 GEMMs
         feat = torch.cat((hidden, cell), 2).transpose(0, 1)
         feat = linear_3xtf32(self.tanh(feat.reshape(feat.size(0), -1)), self.fc2.weight, self.fc2.bias)
         states = self.tanh(out.transpose(0, 1))                              # B x T x H, input of the vocabulary projection

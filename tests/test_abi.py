@@ -14,7 +14,7 @@ def declared_functions():
         if f.endswith(".h"):
             src = open(os.path.join(ROOT, "include", f)).read()
             src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-            names += re.findall(r"^\s*(?:const\s+)?(?:int|long long|char\s*\*|const char\s*\*)\s*(pcd_\w+)\s*\(", src, flags=re.M)
+            names += re.findall(r"^\s*(?:const\s+)?(?:int|long long|size_t|char\s*\*|const char\s*\*)\s*(pcd_\w+)\s*\(", src, flags=re.M)
     return sorted(set(names))
 
 

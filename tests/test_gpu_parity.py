@@ -106,6 +106,28 @@ def test_vocab_cross_entropy_vs_fp64(B, T, K, V):
         P.assert_close(got.double(), r, 5e-5, name)
 
 
+# persistent-kernel LSTM (tcgen05 projections + cooperative recurrence kernels) vs nn.LSTM in fp64
+@pytest.mark.parametrize("T,B,E,H", [(30, 64, 300, 512), (5, 3, 8, 16), (7, 64, 12, 64)])
+def test_lstm_vs_fp64(T, B, E, H):
+    from pcd_ops import lstm_forward
+    g = torch.Generator().manual_seed(T + B + E + H)
+    lstm = torch.nn.LSTM(E, H, 1).to(DEV)
+    x = torch.randn(T, B, E, generator=g).to(DEV).requires_grad_(True)
+    h0 = (0.5 * torch.randn(1, B, H, generator=g)).to(DEV).requires_grad_(True)
+    G1, G2, G3 = (torch.randn(*s, generator=g).to(DEV) for s in ((T, B, H), (1, B, H), (1, B, H)))
+    out, (h, c) = lstm_forward(lstm, x, h0, h0)
+    ((out * G1).sum() + (h * G2).sum() + (c * G3).sum()).backward()
+    got = [out, h, c, x.grad, h0.grad] + [p.grad for p in lstm.parameters()]
+    ref_lstm = torch.nn.LSTM(E, H, 1).to(DEV).double()
+    ref_lstm.load_state_dict({k: v.double() for k, v in lstm.state_dict().items()})
+    xr, hr = x.detach().double().requires_grad_(True), h0.detach().double().requires_grad_(True)
+    outr, (h_r, c_r) = ref_lstm(xr, (hr, hr))
+    ((outr * G1.double()).sum() + (h_r * G2.double()).sum() + (c_r * G3.double()).sum()).backward()
+    ref = [outr, h_r, c_r, xr.grad, hr.grad] + [p.grad for p in ref_lstm.parameters()]
+    for a_, b_, name in zip(got, ref, ("out", "hT", "cT", "dx", "dh0", "dW_ih", "dW_hh", "db_ih", "db_hh")):
+        P.assert_close(a_.double(), b_, 5e-5, name)
+
+
 def test_vqa_model_golden():
     P.vqa_case(DEV)
 
