@@ -49,10 +49,21 @@ __global__ void __launch_bounds__(kT, 1) lstm_fwd_kernel(FwdArgs a) {
     const int b = threadIdx.x & 63, u = threadIdx.x >> 6, unit = u0 + u;
     for (int t = 0; t < a.T; ++t) {
         const float* hprev = t ? a.hs + (long long)(t - 1) * B * H : a.h0;
+        // h_{t-1} -> shared memory with 16-byte cp.async (L2 only: written by other SMs), all copies of a thread in flight at once
         for (int i = threadIdx.x; i < B * H4; i += kT) {
             const int bb = i / H4, k4 = i - bb * H4;
-            *reinterpret_cast<float4*>(Hs + bb * HP + 4 * k4) = __ldcg(reinterpret_cast<const float4*>(hprev + (long long)bb * H + 4 * k4));
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Hs + bb * HP + 4 * k4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(hprev + (long long)bb * H + 4 * k4) : "memory");
         }
+        // this thread's input-projection terms and previous cell state: issued before the wait so their latency overlaps
+        float gxv[4] = {0.f, 0.f, 0.f, 0.f}, cprev = 0.f;
+        if (b < B) {
+            const long long row = (long long)t * B + b;
+            const float* g = a.gx + row * 4 * H;
+            gxv[0] = g[unit]; gxv[1] = g[H + unit]; gxv[2] = g[2 * H + unit]; gxv[3] = g[3 * H + unit];
+            cprev = t ? a.cs[(row - B) * H + unit] : a.c0[(long long)b * H + unit];
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         if (b < B) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -67,10 +78,8 @@ __global__ void __launch_bounds__(kT, 1) lstm_fwd_kernel(FwdArgs a) {
                 }
             }
             const long long row = (long long)t * B + b;
-            const float* g = a.gx + row * 4 * H;
-            const float gi = sigm(acc[0] + g[unit]), gf = sigm(acc[1] + g[H + unit]);
-            const float gg = tanhf(acc[2] + g[2 * H + unit]), go = sigm(acc[3] + g[3 * H + unit]);
-            const float cprev = t ? a.cs[(row - B) * H + unit] : a.c0[(long long)b * H + unit];
+            const float gi = sigm(acc[0] + gxv[0]), gf = sigm(acc[1] + gxv[1]);
+            const float gg = tanhf(acc[2] + gxv[2]), go = sigm(acc[3] + gxv[3]);
             const float c = fmaf(gf, cprev, gi * gg);
             float* ac = a.act + row * 4 * H;
             ac[unit] = gi; ac[H + unit] = gf; ac[2 * H + unit] = gg; ac[3 * H + unit] = go;
@@ -157,6 +166,7 @@ __global__ void __launch_bounds__(kT, 1) lstm_bwd_kernel(BwdArgs a) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             if (b < B) {
                 const float* src = a.pbuf + (long long)par * G * B * H + (long long)b * H + u0;
+#pragma unroll 8
                 for (int g = gq; g < G; g += 4) {
                     const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long long)g * B * H));
                     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
