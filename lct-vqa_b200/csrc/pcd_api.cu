@@ -226,9 +226,11 @@ static int run_edge_bwd(const EdgeGeom& q, const EdgeG* edges, int n, float eps,
     return PCD_OK;
 }
 
-static int run_source_grad(const SourceGradArgs& a, void* stream) {
-    const int chunks = (a.Hs * a.Ws + 4095) / 4096;
-    return launch<KSourceGrad, SourceGradArgs>(a, chunks, a.C, a.B, 0, stream);
+static int run_source_grad(const SourceGradArgs& a0, void* stream) {
+    SourceGradArgs a = a0;
+    const int HW = a.Hs * a.Ws, chunks = (HW + 4095) / 4096;
+    a.nimg = HW >= 4096 ? 1 : (4096 / HW < a.B ? 4096 / HW : a.B);       // ~4096 pixels (4 float4 per thread) per block
+    return launch<KSourceGrad, SourceGradArgs>(a, chunks, a.C, (a.B + a.nimg - 1) / a.nimg, 0, stream);
 }
 
 // ---- preprocess ------------------------------------------------------------------------------------------
@@ -247,7 +249,7 @@ static int run_pre_forward(int B, int Cin, int Cout, int Hin, int Win, int fr, f
     memset(&nrm, 0, sizeof nrm);
     nrm.B = B; nrm.C = Cout; nrm.HW = HW; nrm.eps = eps; nrm.momentum = mom; nrm.src = y; nrm.dst = y;
     nrm.stats = stats; nrm.running = running; nrm.nbt = nbt;
-    return launch<KNorm, NormArgs>(nrm, (HW + 4095) / 4096, Cout, B, 0, stream);
+    return launch<KNorm, NormArgs>(nrm, norm_grid_x(B, HW), Cout, 1, 0, stream);
 }
 
 static int run_pre_backward(int B, int Cin, int Cout, int Hin, int Win, int fr, float eps, const float* x, const float* w,
@@ -257,7 +259,7 @@ static int run_pre_backward(int B, int Cin, int Cout, int Hin, int Win, int fr, 
     BnBwdStatArgs s;
     memset(&s, 0, sizeof s);
     s.B = B; s.C = Cout; s.HW = HW; s.dy = dy; s.y = y; s.stats = nullptr; s.eps = eps; s.bstats = bstats;
-    PCD_TRY((launch<KBnBwdStats, BnBwdStatArgs>(s, (HW + 4095) / 4096, Cout, B, bn_bwd_stats_smem_floats(), stream)));
+    PCD_TRY((launch<KBnBwdStats, BnBwdStatArgs>(s, norm_grid_x(B, HW), Cout, 1, bn_bwd_stats_smem_floats(), stream)));
     if (!dx && !gw) return PCD_OK;
     PreBwdArgs a;
     memset(&a, 0, sizeof a);
@@ -728,7 +730,7 @@ int pcd_stem_forward(const pcd_stem_args* a, void* stream) {
     n.B = a->batch; n.C = Co; n.HW = HW; n.eps = a->bn_eps; n.momentum = a->bn_momentum; n.src = a->saved_z; n.dst = a->out;
     n.stats = a->stats; n.gamma = a->params + Co * 27; n.bias = a->params + Co * 28; n.running = a->running;
     n.nbt = (long long*)a->nbt;
-    return launch<KNorm, NormArgs>(n, (HW + 4095) / 4096, Co, a->batch, 0, stream);
+    return launch<KNorm, NormArgs>(n, norm_grid_x(a->batch, HW), Co, 1, 0, stream);
 }
 
 int pcd_stem_backward(const pcd_stem_args* a, void* stream) {
@@ -740,7 +742,7 @@ int pcd_stem_backward(const pcd_stem_args* a, void* stream) {
     memset(&s, 0, sizeof s);
     s.B = a->batch; s.C = Co; s.HW = HW; s.dy = a->grad_out; s.y = a->saved_z; s.stats = a->stats; s.eps = a->bn_eps;
     s.bstats = a->bstats;
-    PCD_TRY((launch<KBnBwdStats, BnBwdStatArgs>(s, (HW + 4095) / 4096, Co, a->batch, bn_bwd_stats_smem_floats(), stream)));
+    PCD_TRY((launch<KBnBwdStats, BnBwdStatArgs>(s, norm_grid_x(a->batch, HW), Co, 1, bn_bwd_stats_smem_floats(), stream)));
     if (!a->grad_params) return PCD_OK;
     PCD_TRY(zero_async(a->grad_params, (size_t)Co * 29 * sizeof(float), stream));
     StemBwdArgs b;

@@ -168,22 +168,28 @@ struct SourceGradArgs {
     float* out;            // d source (B, C, Hs, Ws) view
     long long out_ns;
     int nedges;
+    int nimg;              // images per block (blockIdx.z covers ceil(B / nimg)); >1 when planes are small
     SrcEdge e[kMaxSrcEdges];
 };
 
 // d x[:, ch<c]  = g0 + sum_e [ relu'(x) * (A3 + A5 + D3 + D5 (+ FR)) + max-pool + avg-pool(+identity) partials ]
 // d x[:, q*c+j] = g0 + sum_e beta_e * (dN_e[:, 4j+q]  |  routed through the 2x2 max-pool argmax at stride 2)
-PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int n) {
+// block (bx, ch, nz): pixel chunk bx of channel ch for images nz*nimg .. (several images per block when planes are small)
+PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
     const int HW = a.Hs * a.Ws, c = a.C / 4;
     const int p0 = bx * 4096;
     const int npx = (HW - p0) < 4096 ? (HW - p0) : 4096;
-    float* ob = a.out + (long long)n * a.out_ns + (long long)ch * HW;
-    const float* xb = a.x + (long long)n * a.x_ns + (long long)ch * HW;
+    const int nimg = a.nimg > 0 ? a.nimg : 1, n0 = nz * nimg;
     const long long pslot = (long long)a.B * c * HW;
-    const bool vec = (HW % 4 == 0) && (p0 % 4 == 0) && ((((uintptr_t)ob) | ((uintptr_t)xb)) & 15) == 0 &&
-                     (!a.g0 || ((((uintptr_t)(a.g0 + (long long)n * a.g0_ns + (long long)ch * HW)) & 15) == 0));
+    const bool vec = (HW % 4 == 0) && (p0 % 4 == 0) && ((((uintptr_t)a.out) | ((uintptr_t)a.x)) & 15) == 0 &&
+                     a.out_ns % 4 == 0 && a.x_ns % 4 == 0 && (!a.g0 || (((((uintptr_t)a.g0) & 15) == 0) && a.g0_ns % 4 == 0));
+    const int tpp = npx / 4;          // float4 tasks per plane chunk
     if (ch < c && vec) {
-        PCD_FOR(i4, npx / 4) {
+        PCD_FOR(tt, nimg * tpp) {
+            const int n = n0 + tt / tpp, i4 = tt % tpp;
+            if (n >= a.B) continue;
+            float* ob = a.out + (long long)n * a.out_ns + (long long)ch * HW;
+            const float* xb = a.x + (long long)n * a.x_ns + (long long)ch * HW;
             const int p = p0 + i4 * 4;
             F4 v = {0.f, 0.f, 0.f, 0.f};
             if (a.g0) v = *reinterpret_cast<const F4*>(a.g0 + (long long)n * a.g0_ns + (long long)ch * HW + p);
@@ -224,7 +230,11 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int n) {
         vecb = vecb && ((((uintptr_t)a.e[k].dn) & 15) == 0) && a.e[k].dn_ns % 4 == 0 && (a.e[k].stride == 1 || a.Ws % 8 == 0);
     if (vecb) {
         const int q = ch / c, j = ch - q * c;
-        PCD_FOR(i4, npx / 4) {
+        PCD_FOR(tt, nimg * tpp) {
+            const int n = n0 + tt / tpp, i4 = tt % tpp;
+            if (n >= a.B) continue;
+            float* ob = a.out + (long long)n * a.out_ns + (long long)ch * HW;
+            const float* xb = a.x + (long long)n * a.x_ns + (long long)ch * HW;
             const int p = p0 + i4 * 4;
             F4 v = {0.f, 0.f, 0.f, 0.f};
             if (a.g0) v = *reinterpret_cast<const F4*>(a.g0 + (long long)n * a.g0_ns + (long long)ch * HW + p);
@@ -260,7 +270,11 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int n) {
         }
         return;
     }
-    PCD_FOR(i, npx) {
+    PCD_FOR(tt, nimg * npx) {
+        const int n = n0 + tt / npx, i = tt % npx;
+        if (n >= a.B) continue;
+        float* ob = a.out + (long long)n * a.out_ns + (long long)ch * HW;
+        const float* xb = a.x + (long long)n * a.x_ns + (long long)ch * HW;
         const int p = p0 + i;
         float v = a.g0 ? a.g0[(long long)n * a.g0_ns + (long long)ch * HW + p] : 0.f;
         for (int k = 0; k < a.nedges; ++k) {
@@ -365,24 +379,38 @@ struct BnBwdStatArgs {
 
 PCD_HOSTDEV size_t bn_bwd_stats_smem_floats() { return 2 * 1024 + 2 * 32 + 16; }
 
-PCD_HD void bn_bwd_stats_body(const BnBwdStatArgs& a, int bx, int ch, int n, float* smem) {
+// block (bx, ch): 4096 elements of channel ch, flattened over (image, pixel)
+PCD_HD void bn_bwd_stats_body(const BnBwdStatArgs& a, int bx, int ch, int, float* smem) {
     float* P = smem;
     float* P2 = P + 2 * 1024;
-    const long long base = ((long long)n * a.C + ch) * a.HW;
-    const int p0 = bx * 4096;
     float mean = 0.f, rstd = 1.f;
     if (a.stats) {
         BnC b = bn_consts(a.stats, a.C, 0, ch, (double)a.B * a.HW, a.eps);
         mean = b.mean; rstd = b.rstd;
     }
+    const bool vec = (a.HW % 4 == 0) && ((((uintptr_t)a.dy) | ((uintptr_t)a.y)) & 15) == 0;
+    const long long total = (long long)a.B * a.HW;
     PCD_FOR(task, 1024) {
         float s = 0.f, q = 0.f;
-        for (int t = 0; t < 4; ++t) {
-            const int p = p0 + task * 4 + t;
-            if (p < a.HW) {
-                const float d = a.dy[base + p];
-                s += d;
-                q = fmaf(d, (a.y[base + p] - mean) * rstd, q);
+        const long long t0 = (long long)bx * 4096 + 4 * task;
+        if (vec) {
+            if (t0 < total) {
+                const long long n = t0 / a.HW, p = t0 - n * a.HW;
+                const long long o = (n * a.C + ch) * a.HW + p;
+                const F4 d = *reinterpret_cast<const F4*>(a.dy + o), y = *reinterpret_cast<const F4*>(a.y + o);
+                s = (d.x + d.y) + (d.z + d.w);
+                q = fmaf(d.x, (y.x - mean) * rstd, fmaf(d.y, (y.y - mean) * rstd, fmaf(d.z, (y.z - mean) * rstd, d.w * ((y.w - mean) * rstd))));
+            }
+        } else {
+            for (int t = 0; t < 4; ++t) {
+                const long long tt = t0 + t;
+                if (tt < total) {
+                    const long long n = tt / a.HW, p = tt - n * a.HW;
+                    const long long o = (n * a.C + ch) * a.HW + p;
+                    const float d = a.dy[o];
+                    s += d;
+                    q = fmaf(d, (a.y[o] - mean) * rstd, q);
+                }
             }
         }
         P[task] = s;

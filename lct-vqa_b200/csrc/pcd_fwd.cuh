@@ -226,22 +226,44 @@ struct NormArgs {
     long long* nbt;
 };
 
-PCD_HD void norm_body(const NormArgs& a, int bx, int ch, int n) {
+// block (bx, ch): float4 tasks bx*1024 .. +1023 of channel ch, flattened over (image, pixel) when the planes allow float4
+PCD_HD void norm_body(const NormArgs& a, int bx, int ch, int) {
     const double cnt = (double)a.B * a.HW;
     BnC b = bn_consts(a.stats, a.C, 0, ch, cnt, a.eps);
     const float sc = b.rstd * (a.gamma ? a.gamma[ch] : 1.f);
     const float sh = (a.bias ? a.bias[ch] : 0.f) - b.mean * sc;
-    const long long base = ((long long)n * a.C + ch) * a.HW;
-    const int p0 = bx * 4096;
-    const int npx = (a.HW - p0) < 4096 ? (a.HW - p0) : 4096;
-    PCD_FOR(i, npx) a.dst[base + p0 + i] = fmaf(a.src[base + p0 + i], sc, sh);
-    if (bx == 0 && n == 0 && a.running) {
+    const bool vec = (a.HW % 4 == 0) && ((((uintptr_t)a.src) | ((uintptr_t)a.dst)) & 15) == 0;
+    if (vec) {
+        const int HW4 = a.HW / 4, total = a.B * HW4;
+        PCD_FOR(k, 1024) {
+            const int t = bx * 1024 + k;
+            if (t < total) {
+                const int n = t / HW4, p4 = t - n * HW4;
+                const long long o = ((long long)n * a.C + ch) * a.HW + 4 * p4;
+                const F4 v = *reinterpret_cast<const F4*>(a.src + o);
+                F4 r = {fmaf(v.x, sc, sh), fmaf(v.y, sc, sh), fmaf(v.z, sc, sh), fmaf(v.w, sc, sh)};
+                *reinterpret_cast<F4*>(a.dst + o) = r;
+            }
+        }
+    } else {
+        const long long total = (long long)a.B * a.HW;
+        PCD_FOR(k, 4096) {
+            const long long t = (long long)bx * 4096 + k;
+            if (t < total) {
+                const long long n = t / a.HW, p = t - n * a.HW;
+                const long long o = (n * a.C + ch) * a.HW + p;
+                a.dst[o] = fmaf(a.src[o], sc, sh);
+            }
+        }
+    }
+    if (bx == 0 && a.running) {
         PCD_FOR(i, 1) {
             bn_running_update(a.stats, a.C, ch, cnt, a.momentum, a.running);
             if (ch == 0) a.nbt[0] += 1;
         }
     }
 }
+PCD_HOSTDEV int norm_grid_x(int B, int HW) { return (int)(((long long)B * HW + 4095) / 4096); }
 
 // ---- stem: Conv2d(3, Cout, 3, padding=1) (model_search.py:110-113); BN applied by norm_body ----------
 struct StemArgs {
