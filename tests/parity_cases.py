@@ -104,6 +104,39 @@ def network_case(device):
     return net
 
 
+def network_vs_oracle(B, H, device, seed=17):
+    """The whole search network (stem, 4 cells at the production geometries, global pooling) at full batch vs the oracle."""
+    import config
+    config.DEVICE = device
+    from pcdarts.model_search import Network
+    net = Network(16, 10, 4).train()
+    _fill(net, seed)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    par, buf = O.split_state(sd)
+    for v in par.values():
+        v.requires_grad_(True)
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, H, H, generator=gen)
+    arch = [1e-1 * torch.randn(s, generator=gen) for s in ((14, 8), (14, 8), (14,), (14,))]
+    G = torch.randn(B, 256 * 49, generator=gen)
+    ra = [a.clone().requires_grad_(True) for a in arch]
+    yr = O.network_forward(par, O.BNState(buf), ra, x)
+    (yr * G).sum().backward()
+    net.to(device)
+    for a, v in zip(net.arch_parameters(), arch):
+        a.data.copy_(v)
+    y = net(x.to(device))
+    assert_close(y, yr, REL_TOL, "y")
+    (y * G.to(device)).sum().backward()
+    for i, (a, r) in enumerate(zip(net.arch_parameters(), ra)):
+        assert_close(a.grad, r.grad, REL_TOL, f"darch{i}")
+    for k, p_ in net.named_parameters():
+        assert_close(p_.grad, par[k].grad, REL_TOL, k)
+    for k, v in net.state_dict().items():
+        if "running" in k:
+            assert_close(v, buf[k], 1e-5, k)
+
+
 def shuffle_case(device):
     from pcdarts.model_search import channel_shuffle
     g = load_golden("shuffle")

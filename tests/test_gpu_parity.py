@@ -23,6 +23,11 @@ def test_network_golden():
     P.network_case(DEV)
 
 
+def test_network_full_size_vs_oracle():
+    """BASELINE.json configuration: C=16, 4 cells, 64x64 images, batch 64 — outputs, every weight grad, alpha/beta grads."""
+    P.network_vs_oracle(64, 64, DEV)
+
+
 def test_shuffle_bit_exact():
     P.shuffle_case(DEV)
 
