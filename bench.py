@@ -31,6 +31,7 @@ for p in (PKG, ROOT):
 
 import torch  # noqa: E402
 
+_REAL_STDOUT = 1
 METRIC = "search steps/sec (w+alpha step)"
 UNIT = "steps/s"
 DIMS = dict(embed_size=512, ans_vocab_size=1000, word_embed_size=300, num_layers=1, hidden_size=512)
@@ -54,7 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
-    ap.add_argument("--graph-dp", action="store_true", help="capture the step in a CUDA graph under data parallelism too (NCCL all-reduces inside the graph)")
+    ap.add_argument("--no-graph-dp", action="store_true", help="under data parallelism run the step eagerly instead of as a CUDA graph with the NCCL all-reduces captured inside")
     ap.add_argument("--no-overlap", action="store_true", help="keep the weight-grad jobs on the main stream")
     return ap.parse_args()
 
@@ -137,11 +138,11 @@ def run_reference(a):
     if rank != 0:
         return
     value, dt, cb = time_cpu(a, a.steps, a.warmup, budget_s=150.0)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload(a, a.gpus), "cpu_baseline": cb,
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -219,7 +220,7 @@ def run_b200(a):
     if world > 1:           # identical replicas: rank 0's init everywhere
         for t in list(model.parameters()) + list(model.buffers()) + list(model.arch_parameters()):
             dist.broadcast(t.data, 0)
-    use_graph = not a.no_graph and (world == 1 or a.graph_dp)
+    use_graph = not a.no_graph and (world == 1 or not a.no_graph_dp)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph)
     architect = Architect(model, Namespace(arch_learn_rate=6e-4, arch_wt_decay=1e-3, qst_only=False), reducer=reducer)
     if use_graph:
@@ -343,9 +344,16 @@ def run_b200(a):
                "data": "synthetic", "config": workload(a, world), "e2e": e2e, "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
                "wgrad_overlap": not a.no_overlap, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
                "comm": None if reducer is None else {"allreduce_calls": reducer.calls, "allreduce_bytes": reducer.bytes}}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
+        if use_graph:
+            # NCCL kernels live inside the captured graph: tearing the communicator down under it hung once
+            # (profiles/r01_bench_dp2_graph.json run); every rank has reported, so leave without the teardown
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -382,8 +390,16 @@ def mixedop_microbench(dev, B, hbm):
     return res
 
 
+def emit(obj):
+    """The ONE JSON line, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 if __name__ == "__main__":
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)              # NCCL's version banner and any library chatter: stderr, not the JSON channel
     if args.impl == "reference":
         run_reference(args)
     else:
