@@ -316,10 +316,9 @@ def run_b200(a):
         roofline = {"bound": "hbm", "kernel": "MixedOp kernel group (fwdA,fwdB,combine | node_stats,bwdB,bwdA,wgrad,"
                                               "source_grad,arch_grads): all 56 edges x all passes of one step",
                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                    # DRAM bytes of the same kernel group from ncu (dram__bytes_read + dram__bytes_write, cold cache, one
-                    # forward + one full backward = 10.39 GB, of which 1.87 GB weight-grad jobs: profiles/r01_v5_ncu_launches_summary.txt)
-                    "traffic": ((n_fwd * 3.0 + (n_bwd - n_fwd) * 0.0) * 0 + (3 if unrolled else 2) * 10.39e9 +
-                                (2 if unrolled else 0) * (10.39e9 - 1.87e9)) * a.batch / 64.0,
+                    # DRAM bytes of the same kernel group from ncu (dram__bytes_read + dram__bytes_write, cold cache): one forward
+                    # + one full backward = 9.15 GB, of which 1.88 GB weight-grad jobs (profiles/r01_v6_ncu_launches_summary.txt)
+                    "traffic": ((3 if unrolled else 2) * 9.15e9 + (2 if unrolled else 0) * (9.15e9 - 1.88e9)) * a.batch / 64.0,
                     "traffic_note": "bytes per step of the kernel group, ncu cold-cache DRAM counters at B=64 scaled by B/64",
                     "algorithmic_mb_per_step": alg_mb, "kernel_ms_per_step": mixed_ms, "peak_source": peak_src,
                     "passes_per_step": {"forward": n_fwd, "backward": n_bwd},
@@ -330,6 +329,9 @@ def run_b200(a):
     if not a.no_extras:
         if rank == 0:
             extras["mixedop_fwd_bwd"] = mixedop_microbench(dev, a.batch, hbm)
+            # roofline sweep of a single MixedOp at larger per-GPU batches (one edge at B=64 is latency-bound)
+            extras["mixedop_fwd_bwd_b256"] = mixedop_microbench(dev, 256, hbm)
+            extras["mixedop_fwd_bwd_b512"] = mixedop_microbench(dev, 512, hbm)
         if True:
             w_ms = timed(lambda: stepper.w_step(*train), max(3, a.steps // 2)) / max(3, a.steps // 2)
             fo_ms = timed(lambda: stepper.step(train, valid, 1e-3, unrolled=False), max(3, a.steps // 2)) / max(3, a.steps // 2)
