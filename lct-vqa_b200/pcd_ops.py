@@ -492,6 +492,9 @@ def _gemm_tn(lib, a, lda, b, ldb, c, ldc, m, n, k, bias, split_k, ref):
                                         N.stream_for(ref)), "pcd_gemm_tn_3xtf32")
 
 
+_TC_MIN_FLOP = 5e8      # below this a projection stays on the library SGEMM (measured: the 64-row heads lose ~1 ms/step on the TMA path)
+
+
 def _auto_split(m, n, k):
     """Split K over blockIdx.z when the output has too few 128 x 256 tiles to fill 148 SMs (keeps >= 8 k-blocks per split)."""
     tiles = ((m + 127) // 128) * ((n + 255) // 256)
@@ -554,6 +557,10 @@ class Linear3xTF32Function(torch.autograd.Function):
 def linear_3xtf32(x, weight, bias):
     """nn.Linear forward on the tensor cores when the shapes allow TMA (rows and depth multiples of 4), else F.linear."""
     if x.shape[-1] % 4 or not (x.is_cuda or N._emu_lib is not None):
+        return torch.nn.functional.linear(x, weight, bias)
+    m = x.numel() // x.shape[-1]
+    if x.is_cuda and 2.0 * m * weight.shape[0] * weight.shape[1] < _TC_MIN_FLOP:
+        # tiny products are launch/latency-bound either way; the TMA path adds operand transposes in the backward
         return torch.nn.functional.linear(x, weight, bias)
     return Linear3xTF32Function.apply(x, weight, bias)
 
