@@ -23,3 +23,5 @@ BATCH_SIZE = 64
 ARCH_TYPE = 'darts'
 SKIP_STAGE2 = False
 SKIP_STAGE3 = True
+W_LAMBDA = 1.0                # basic_vqa/config.py:74  weight of the pseudo-QA soft loss of the W model
+PRETRAIN_ENC = True           # basic_vqa model_factory: VGG19 of the W model / fixed EF encoder starts from ImageNet weights

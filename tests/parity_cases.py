@@ -384,3 +384,64 @@ def wstep_case(device):
     for k in g:
         if k.startswith("param."):
             assert_close(named[k[6:]].detach(), g[k], REL_TOL, k)
+
+
+# ---- 3-stage LCT alpha-step (golden: tests/golden/make_golden_lct.py) ------------------------------------------------
+LCT_DIMS = dict(embed_size=16, qst_vocab_size=40, ans_vocab_size=12, word_embed_size=8, num_layers=1, hidden_size=16)
+
+
+def lct_batch(seed, device, B=2, H=32):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(B, 3, H, H, generator=g)
+    qst = torch.randint(0, LCT_DIMS["qst_vocab_size"], (B, 30), generator=g)
+    qst[:, 0] = 2
+    lbl = torch.randint(0, LCT_DIMS["ans_vocab_size"], (B,), generator=g)
+    return img.to(device), qst.to(device), lbl.to(device)
+
+
+def architect_lct_case(device):
+    """ArchitectLct.step (EF on the search-network kernels, W = VGG19 stock torch) vs the reference's own run."""
+    import config
+    config.DEVICE = device
+    config.ARCH_TYPE = "darts"
+    from models import VqaModel as WModel
+    from models_lct import VqaModel as EfModel
+    from architect_factory import get_architect
+    g = load_golden("architect_lct")
+    ef = EfModel(**LCT_DIMS)
+    w = WModel(pretrained=False, **LCT_DIMS)
+    for m, seed in ((ef, 500), (w, 600)):
+        _fill(m, seed)
+        for mod in m.modules():                 # includes the two Dropout layers inside torchvision's VGG19 classifier
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        m.to(device).train()
+    gen = torch.Generator().manual_seed(77)
+    for a in ef.arch_parameters():
+        a.data.copy_((1e-1 * torch.randn(a.shape, generator=gen)).to(device))
+    ef_opt = torch.optim.Adam(ef.parameters(), lr=1e-3)
+    w_opt = torch.optim.Adam(w.parameters(), lr=1e-3)
+    arch = get_architect(ef, w, ef_opt, w_opt)
+    assert type(arch).__name__ == "ArchitectLct"
+    arch.step(*lct_batch(21, device), *lct_batch(22, device), 1e-3, 1e-3)
+    L = arch.last
+    assert abs(L["unrolled_loss"].item() - float(g["loss.grad_wprime"])) <= 1e-4 * abs(float(g["loss.grad_wprime"]))
+    assert abs(L["grad_wprime_norm"].item() - float(g["norm.grad_wprime"])) <= 1e-4 * float(g["norm.grad_wprime"])
+    # kappa is a finite difference of EF' gradients: only its scale enters the next stage (R = r / |kappa|)
+    for key, ref in (("kappa_p", "norm.kappa_p"), ("kappa_n", "norm.kappa_n")):
+        n = torch.cat([t.reshape(-1) for t in L[key]]).norm().item()
+        assert abs(n - float(g[ref])) <= 1e-4 * float(g[ref]), (key, n, float(g[ref]))
+    # gradients at EF +- R kappa: plain gradients, rel 1e-3 (the perturbation direction itself is a noisy finite difference)
+    gmax = 0.0
+    for i in range(4):
+        assert_close(L["gamma_p"][i], g[f"gamma_p{i}"], 1e-3, f"gamma_p{i}")
+        assert_close(L["gamma_n"][i], g[f"gamma_n{i}"], 1e-3, f"gamma_n{i}")
+        gmax = max(gmax, g[f"gamma_p{i}"].abs().max().item() + g[f"gamma_n{i}"].abs().max().item())
+    # final arch grads = (g+ - g-) / 2R * ef_lr * w_lr: cancellation-aware bound (SURVEY.md App. C)
+    R = L["gamma_R"].item()
+    bound = 1e-3 * gmax / (2 * R) * 1e-3 * 1e-3
+    for i, a in enumerate(ef.arch_parameters()):
+        d = (a.grad.detach().cpu() - g[f"darch{i}"]).abs().max().item()
+        assert d <= bound, (i, d, bound)
+        assert_close(a.data, g[f"arch_after{i}"], 1e-5, f"arch_after{i}")
+    return arch

@@ -68,6 +68,10 @@ def test_w_step_emulated():
     P.wstep_case("cpu")
 
 
+def test_architect_lct_emulated():
+    P.architect_lct_case("cpu")
+
+
 def test_product_refuses_cpu_without_emulation():
     import pcd_native
     keep, pcd_native._emu_lib = pcd_native._emu_lib, None

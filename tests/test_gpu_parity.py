@@ -135,6 +135,11 @@ def test_lstm_vs_fp64(T, B, E, H):
         P.assert_close(a_.double(), b_, 5e-5, name)
 
 
+def test_architect_lct_golden():
+    """3-stage LCT alpha-step (architect_lct.py:32-92): EF passes on the sm_100a kernels, W = VGG19 in stock torch."""
+    P.architect_lct_case(DEV)
+
+
 def test_vqa_model_golden():
     P.vqa_case(DEV)
 
