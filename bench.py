@@ -337,6 +337,12 @@ def run_b200(a):
             fo_ms = timed(lambda: stepper.step(train, valid, 1e-3, unrolled=False), max(3, a.steps // 2)) / max(3, a.steps // 2)
             extras["w_step_only_steps_per_s"] = world * 1e3 / w_ms
             extras["w_plus_first_order_alpha_steps_per_s"] = world * 1e3 / fo_ms
+    if rank == 0 and world == 1 and not a.no_extras:
+        # BASELINE.json configs[2]: the 3-stage LCT alpha-step (6 forward / 5 backward search-net passes + VGG19 W model), eager
+        try:
+            extras["lct_alpha_step"] = lct_alpha_step_bench(a, dev)
+        except Exception as e:      # the headline numbers above do not depend on it
+            extras["lct_alpha_step"] = {"error": repr(e)[:200]}
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         _, _, cpu = time_cpu(a, 1, 0, budget_s=20.0)
@@ -357,6 +363,34 @@ def run_b200(a):
             sys.stderr.flush()
             os._exit(0)
         dist.destroy_process_group()
+
+
+def lct_alpha_step_bench(a, dev, iters=3):
+    """ArchitectLct.step (basic_vqa/pcdarts/architect_lct.py:32-92) at the reference's default sizes: EF = PC-DARTS VqaModel on
+    the kernels, W = VGG19 VqaModel (random weights: no download), B = 64, deterministic question sampling."""
+    import config
+    from architect_factory import get_architect
+    from models import VqaModel as WModel
+    from models_lct import VqaModel as EfModel
+    config.ARCH_TYPE = "darts"
+    torch.manual_seed(10)
+    dims = dict(DIMS, qst_vocab_size=a.vocab)
+    ef = EfModel(**dims).to(dev).train()
+    w = WModel(pretrained=False, **dims).to(dev).train()
+    arch = get_architect(ef, w, torch.optim.Adam(ef.parameters(), lr=1e-3), torch.optim.Adam(w.parameters(), lr=1e-3))
+    tr = [t.to(dev) for t in synth_batch(10, a.batch, a.vocab, a.img)]
+    va = [t.to(dev) for t in synth_batch(11, a.batch, a.vocab, a.img)]
+    arch.step(*tr, *va, 1e-3, 1e-3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        arch.step(*tr, *va, 1e-3, 1e-3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"ms_per_alpha_step": ms, "alpha_steps_per_s": 1e3 / ms, "batch": a.batch, "mode": "eager (no CUDA graph)",
+            "w_val_loss": float(arch.last["unrolled_loss"])}
 
 
 def mixedop_microbench(dev, B, hbm):

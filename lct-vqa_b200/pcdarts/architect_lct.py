@@ -39,6 +39,7 @@ class ArchitectLct(object):
         self.ef_optimizer = ef_optimizer
         self.w_optimizer = w_optimizer
         self.last = {}          # intermediate quantities of the last step (tests, logging)
+        self._twins = {}        # source model id -> persistent unrolled twin
 
     def step(self, img_train, qst_train, label_train, img_valid, qst_valid, label_valid, ef_lr, w_lr):
         self.ef_optimizer.zero_grad()
@@ -96,17 +97,30 @@ class ArchitectLct(object):
         return self._construct_model_from_theta(theta.sub(moment + dtheta, alpha=eta), model)
 
     def _construct_model_from_theta(self, theta, model):
-        model_new = model.new()
-        model_dict = model.state_dict()
-        params, offset = {}, 0
-        for k, v in model.named_parameters():
-            n = v.numel()
-            params[k] = theta[offset: offset + n].view(v.size())
-            offset += n
-        assert offset == len(theta)
-        model_dict.update(params)
-        model_new.load_state_dict(model_dict)
-        return model_new.to(config.DEVICE)
+        """model.new() + load_state_dict(model's buffers, theta as parameters) (architect_lct.py:142-156).  The reference
+        builds a fresh model (for W: a whole VGG19) on every call; here the twin is built once per source model and
+        refilled in place — same parameters, same buffers, same dropout configuration."""
+        twin = self._twins.get(id(model))
+        if twin is None:
+            twin = model.new().to(config.DEVICE)
+            self._twins[id(model)] = twin
+        with torch.no_grad():
+            src_buf, dst_buf = dict(model.named_buffers()), dict(twin.named_buffers())
+            if src_buf:
+                keys = [k for k in dst_buf if k in src_buf]
+                torch._foreach_copy_([dst_buf[k] for k in keys], [src_buf[k] for k in keys])
+            views, offset = [], 0
+            params = list(twin.parameters())
+            for v in params:
+                n = v.numel()
+                views.append(theta[offset: offset + n].view(v.size()))
+                offset += n
+            assert offset == len(theta)
+            torch._foreach_copy_([p.data for p in params], views)
+            if hasattr(model, "arch_parameters"):       # Network.new() copies the current alphas / betas (model_search.py:138-143)
+                torch._foreach_copy_([t.data for t in twin.arch_parameters()], [t.data for t in model.arch_parameters()])
+        twin.train(model.training)
+        return twin
 
     def _calc_grad(self, loss, param_fn, exp_zero_grad=0):
         grads = list(torch.autograd.grad(loss, list(param_fn()), allow_unused=True))

@@ -444,4 +444,9 @@ def architect_lct_case(device):
         d = (a.grad.detach().cpu() - g[f"darch{i}"]).abs().max().item()
         assert d <= bound, (i, d, bound)
         assert_close(a.data, g[f"arch_after{i}"], 1e-5, f"arch_after{i}")
+    # a second step reuses the persistent twins: they must pick up the alphas the first step just changed
+    before = [a.detach().clone() for a in ef.arch_parameters()]
+    arch.step(*lct_batch(21, device), *lct_batch(22, device), 1e-3, 1e-3)
+    for tw_a, a in zip(arch._twins[id(ef)].arch_parameters(), before):
+        assert torch.equal(tw_a.detach(), a)
     return arch
