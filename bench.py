@@ -389,8 +389,23 @@ def lct_alpha_step_bench(a, dev, iters=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    return {"ms_per_alpha_step": ms, "alpha_steps_per_s": 1e3 / ms, "batch": a.batch, "mode": "eager (no CUDA graph)",
-            "w_val_loss": float(arch.last["unrolled_loss"])}
+    res = {"ms_per_alpha_step_eager": ms, "batch": a.batch, "w_val_loss": float(arch.last["unrolled_loss"]),
+           "passes": "6 fwd + 5 bwd search-net, 3 greedy decodes, VGG19 W-model (stock torch) unroll + 2 HVP passes"}
+    try:
+        from search import GraphedLctStep
+        g = GraphedLctStep(arch, tr, va, 1e-3, 1e-3)
+        g()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            g()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_g = e0.elapsed_time(e1) / iters
+        res.update(ms_per_alpha_step=ms_g, alpha_steps_per_s=1e3 / ms_g, mode="CUDA graph", w_val_loss_graph=float(g.loss))
+    except Exception as e:
+        res.update(ms_per_alpha_step=ms, alpha_steps_per_s=1e3 / ms, mode="eager (graph capture failed: %s)" % repr(e)[:160])
+    return res
 
 
 def mixedop_microbench(dev, B, hbm):

@@ -17,6 +17,7 @@ import torch
 import torch.nn.functional as F
 
 import config
+import pcd_ops
 
 
 def _concat(xs):
@@ -40,6 +41,7 @@ class ArchitectLct(object):
         self.w_optimizer = w_optimizer
         self.last = {}          # intermediate quantities of the last step (tests, logging)
         self._twins = {}        # source model id -> persistent unrolled twin
+        self.device_scalars = False     # True: no host reads inside step() (CUDA-graph capture)
 
     def step(self, img_train, qst_train, label_train, img_valid, qst_valid, label_valid, ef_lr, w_lr):
         self.ef_optimizer.zero_grad()
@@ -48,6 +50,7 @@ class ArchitectLct(object):
         self.last = {}
         # second-order (unrolled) unconditionally: a first-order approximation does not exist for this objective
         self._backward_step_unrolled(img_train, qst_train, label_train, img_valid, qst_valid, label_valid, ef_lr, w_lr)
+        pcd_ops.overlap_join(img_train)       # no deferred weight-grad job of this step outlives it
         self.optimizer.step()
 
     def _backward_step_unrolled(self, img_train, qst_train, label_train, img_valid, qst_valid, label_valid, ef_lr, w_lr):
@@ -77,7 +80,8 @@ class ArchitectLct(object):
                 v.grad.data.copy_(g.detach() * ef_lr * w_lr)
         self.last.update(unrolled_loss=unrolled_loss.detach(), kappa_norm=_concat(kappa).norm().detach(),
                          grad_wprime_norm=_concat(grad_wprime).norm().detach())
-        logging.info("| TRAIN SET | STAGE3 | W'-Val-Loss: {:.4f}".format(unrolled_loss.item()))
+        if not self.device_scalars:
+            logging.info("| TRAIN SET | STAGE3 | W'-Val-Loss: {:.4f}".format(unrolled_loss.item()))
 
     def _compute_unrolled_model(self, img, qst, label, eta, optimizer, model, loss_fn, exp_zero_grad=0, weight_decay=0, momentum=0):
         loss = loss_fn(img, qst, label)
@@ -135,30 +139,45 @@ class ArchitectLct(object):
         self.last.setdefault("calls", []).append((loss.detach(), _concat(grads).norm().detach()))
         return grads
 
+    def _perturb(self, params, vector, R):
+        """Returns shift(k): params += k * R * vector.  With `device_scalars` R stays a 0-dim device tensor (R * v is formed
+        once), so the step has no host synchronisation and can be captured in a CUDA graph (search.GraphedLctStep)."""
+        data = [p.data for p in params]
+        if self.device_scalars:
+            step_v = torch._foreach_mul(list(vector), R)
+            return lambda k: torch._foreach_add_(data, step_v, alpha=float(k))
+        Rf = R.item()
+        return lambda k: torch._foreach_add_(data, list(vector), alpha=k * Rf)
+
     def _hessian_vector_product(self, vector, img, qa_fn, model, loss_fn, param_fn, r=1e-2, exp_zero_grad=0):
         R = r / _concat(vector).norm()
-        params = list(model.parameters())
-        torch._foreach_add_([p.data for p in params], list(vector), alpha=R.item())
+        shift = self._perturb(list(model.parameters()), vector, R)
+        # only d/d(alpha, beta) is wanted at EF +- R kappa: activation-only backward passes, no weight-grad jobs
+        arch_ids = {id(t) for t in model.arch_parameters()} if hasattr(model, "arch_parameters") else set()
+        wgrads = not all(id(t) in arch_ids for t in param_fn())
+        shift(1)
         qst, ans = qa_fn()
-        grads_p = self._calc_grad(loss_fn(img, qst, ans), param_fn, exp_zero_grad)
-        torch._foreach_add_([p.data for p in params], list(vector), alpha=-2 * R.item())
+        with pcd_ops.weight_grads(wgrads):
+            grads_p = self._calc_grad(loss_fn(img, qst, ans), param_fn, exp_zero_grad)
+        shift(-2)
         qst, ans = qa_fn()
-        grads_n = self._calc_grad(loss_fn(img, qst, ans), param_fn, exp_zero_grad)
-        torch._foreach_add_([p.data for p in params], list(vector), alpha=R.item())
+        with pcd_ops.weight_grads(wgrads):
+            grads_n = self._calc_grad(loss_fn(img, qst, ans), param_fn, exp_zero_grad)
+        shift(1)
         self.last.update(gamma_p=grads_p, gamma_n=grads_n, gamma_R=R.detach())
         return [(x - y).div_(2 * R) for x, y in zip(grads_p, grads_n)]
 
     def _hessian_vector_product_2(self, vector, img, qa_fn, pseudo_qa_fn, model, loss_fn, param_fn, r=1e-2, exp_zero_grad=0):
         R = r / _concat(vector).norm()
-        params = list(model.parameters())
-        torch._foreach_add_([p.data for p in params], list(vector), alpha=R.item())
+        shift = self._perturb(list(model.parameters()), vector, R)
+        shift(1)
         qst, ans = qa_fn()
         pseudo_qst, pseudo_ans = pseudo_qa_fn()
         grads_p = self._calc_grad(loss_fn(img, qst, ans, pseudo_qst, pseudo_ans), param_fn, exp_zero_grad)
-        torch._foreach_add_([p.data for p in params], list(vector), alpha=-2 * R.item())
+        shift(-2)
         qst, ans = qa_fn()
         pseudo_qst, pseudo_ans = pseudo_qa_fn()
         grads_n = self._calc_grad(loss_fn(img, qst, ans, pseudo_qst, pseudo_ans), param_fn, exp_zero_grad)
-        torch._foreach_add_([p.data for p in params], list(vector), alpha=R.item())
+        shift(1)
         self.last.update(kappa_p=grads_p, kappa_n=grads_n, kappa_R=R.detach())
         return [(x - y).div_(2 * R) for x, y in zip(grads_p, grads_n)]

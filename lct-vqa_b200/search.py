@@ -75,3 +75,45 @@ class GraphedSearchStep:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+
+def make_capturable(optimizer):
+    """Adam keeps `step` on the host unless capturable; flip an existing optimizer (state included) to the device form."""
+    for group in optimizer.param_groups:
+        group["capturable"] = True
+        for p in group["params"]:
+            st = optimizer.state.get(p)
+            if st and torch.is_tensor(st.get("step")) and st["step"].device != p.device:
+                st["step"] = st["step"].to(p.device)
+
+
+class GraphedLctStep:
+    """ArchitectLct.step (basic_vqa/pcdarts/architect_lct.py:32-92: 6 forward / 5 backward search-net passes, 3 greedy decodes,
+    the W-model passes and the two finite-difference HVPs) captured once in a CUDA graph and replayed.  The learning rates are
+    baked in at capture; question sampling must be deterministic (argmax) — multinomial sampling draws on the host."""
+
+    def __init__(self, architect, train_batch, valid_batch, ef_lr, w_lr, warmup=2):
+        self.architect = architect
+        self.train = [t.clone() for t in train_batch]
+        self.valid = [t.clone() for t in valid_batch]
+        architect.device_scalars = True
+        make_capturable(architect.optimizer)
+        side = torch.cuda.Stream(priority=-1)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                architect.step(*self.train, *self.valid, ef_lr, w_lr)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            architect.step(*self.train, *self.valid, ef_lr, w_lr)
+        self.loss = architect.last["unrolled_loss"]
+
+    def __call__(self, train_batch=None, valid_batch=None):
+        for dst_list, src_list in ((self.train, train_batch), (self.valid, valid_batch)):
+            if src_list is not None:
+                for dst, src in zip(dst_list, src_list):
+                    dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -399,15 +399,14 @@ def lct_batch(seed, device, B=2, H=32):
     return img.to(device), qst.to(device), lbl.to(device)
 
 
-def architect_lct_case(device):
-    """ArchitectLct.step (EF on the search-network kernels, W = VGG19 stock torch) vs the reference's own run."""
+def make_lct(device):
+    """EF (PC-DARTS VqaModel on the kernels) + W (VGG19 VqaModel, stock torch) + ArchitectLct at the golden case's state."""
     import config
     config.DEVICE = device
     config.ARCH_TYPE = "darts"
     from models import VqaModel as WModel
     from models_lct import VqaModel as EfModel
     from architect_factory import get_architect
-    g = load_golden("architect_lct")
     ef = EfModel(**LCT_DIMS)
     w = WModel(pretrained=False, **LCT_DIMS)
     for m, seed in ((ef, 500), (w, 600)):
@@ -423,6 +422,13 @@ def architect_lct_case(device):
     w_opt = torch.optim.Adam(w.parameters(), lr=1e-3)
     arch = get_architect(ef, w, ef_opt, w_opt)
     assert type(arch).__name__ == "ArchitectLct"
+    return ef, w, arch
+
+
+def architect_lct_case(device):
+    """ArchitectLct.step (EF on the search-network kernels, W = VGG19 stock torch) vs the reference's own run."""
+    g = load_golden("architect_lct")
+    ef, w, arch = make_lct(device)
     arch.step(*lct_batch(21, device), *lct_batch(22, device), 1e-3, 1e-3)
     L = arch.last
     assert abs(L["unrolled_loss"].item() - float(g["loss.grad_wprime"])) <= 1e-4 * abs(float(g["loss.grad_wprime"]))

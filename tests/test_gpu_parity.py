@@ -209,6 +209,44 @@ def test_graphed_unrolled_step_runs():
             assert_close(x.grad, y.grad, 5e-3, "arch grad")
 
 
+def test_graphed_lct_step_matches_eager():
+    """ArchitectLct.step replayed from a CUDA graph (search.GraphedLctStep) == the eager step.  The architecture learning
+    rate is 0 so both copies stay at the same alphas; the finite-difference stages are compared at their own noise level."""
+    import config
+    from helpers import assert_close
+    from search import GraphedLctStep
+    lr0, wd0 = config.ARCH_LEARNING_RATE, config.ARCH_WEIGHT_DECAY
+    config.ARCH_LEARNING_RATE, config.ARCH_WEIGHT_DECAY = 0.0, 0.0
+    try:
+        ef1, w1, eager = P.make_lct(DEV)
+        ef2, w2, arch2 = P.make_lct(DEV)
+    finally:
+        config.ARCH_LEARNING_RATE, config.ARCH_WEIGHT_DECAY = lr0, wd0
+    tr, va = P.lct_batch(21, DEV), P.lct_batch(22, DEV)
+    import pcd_ops
+    pcd_ops.set_wgrad_overlap(True)          # deferred weight-grad jobs on the side stream must be joined inside the capture
+    try:
+        graphed = GraphedLctStep(arch2, tr, va, 1e-3, 1e-3, warmup=2)
+    finally:
+        pcd_ops.set_wgrad_overlap(False)
+    for _ in range(2):
+        eager.step(*tr, *va, 1e-3, 1e-3)
+    for train, valid in ((tr, va), (P.lct_batch(23, DEV), P.lct_batch(24, DEV))):
+        eager.step(*train, *valid, 1e-3, 1e-3)
+        graphed(train, valid)
+        torch.cuda.synchronize()
+        Le, Lg = eager.last, arch2.last
+        assert_close(Lg["unrolled_loss"], Le["unrolled_loss"], 1e-5, "W' validation loss")
+        assert_close(Lg["grad_wprime_norm"], Le["grad_wprime_norm"], 1e-4, "|grad W'|")
+        for key in ("kappa_p", "kappa_n"):
+            ne = torch.cat([t.reshape(-1) for t in Le[key]]).norm()
+            ng = torch.cat([t.reshape(-1) for t in Lg[key]]).norm()
+            assert_close(ng, ne, 1e-4, key)
+        for i in range(4):
+            assert_close(Lg["gamma_p"][i], Le["gamma_p"][i], 1e-3, f"gamma_p{i}")
+            assert_close(Lg["gamma_n"][i], Le["gamma_n"][i], 1e-3, f"gamma_n{i}")
+
+
 def test_native_library_is_the_one_running():
     import pcd_native
     lib = pcd_native.load_cuda()
