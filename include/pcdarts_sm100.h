@@ -301,6 +301,18 @@ int pcd_lstm_backward(int T, int B, int H, const float* dhs, const float* dhT, c
                       const float* cs, const float* c0, const float* w_hh, float* dgates, float* dh0, float* dc0,
                       float* pbuf, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Greedy question decode: replaces QstEncoder.generate's 30-iteration loop of embedding -> nn.LSTM step -> tanh -> Linear(H, V)
+ * -> argmax (darts_vqa/vqa_model.py:103-136, basic_vqa/models_lct.py:124-157, deterministic sampling) with one persistent
+ * cooperative kernel.  The first input is tanh(emb[start_token]), later inputs emb[previous word] (no tanh: vqa_model.py:133);
+ * gate order i, f, g, o; ties in the argmax go to the lowest index.  tokens: [B][T] int64.  B <= 64, H a multiple of 32 up to
+ * 512, E a multiple of 4.  work: pcd_decode_work_floats(B, H, V) floats, 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pcd_decode_work_floats(int B, int H, int V);
+int pcd_decode_greedy(int T, int B, int H, int E, int V, int start_token, const float* emb, const float* w_ih,
+                      const float* w_hh, const float* b_ih, const float* b_hh, const float* h0, const float* c0,
+                      const float* w_out, const float* b_out, long long* tokens, float* work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 import config
-from pcd_ops import linear_3xtf32, lstm_forward, vocab_cross_entropy
+from pcd_ops import decode_greedy, decode_supported, linear_3xtf32, lstm_forward, vocab_cross_entropy
 from pcdarts.model_search import Network
 
 
@@ -73,6 +73,9 @@ class QstEncoder(nn.Module):
     def generate(self, image_embedding):
         """Greedy / sampled 30-step decode from <start> = 2 (models_lct.py:124-157); the word choice is not differentiable."""
         batch = len(image_embedding)
+        h0 = image_embedding.reshape(batch, self.hidden_size)
+        if self.deterministic and decode_supported(h0, self.lstm, self.word2vec, self.fc2):
+            return decode_greedy(h0, self.lstm, self.word2vec, self.fc2, self.max_length)      # one persistent kernel
         self.lstm.flatten_parameters()
         h = image_embedding.view(1, -1, self.hidden_size)
         state = (h, h)

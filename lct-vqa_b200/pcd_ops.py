@@ -714,3 +714,30 @@ def lstm_forward(lstm, x, h0, c0):
         return out, (h, c)
     out, hT, cT = LstmFunction.apply(x, h0[0], c0[0], lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)
     return out, (hT.unsqueeze(0), cT.unsqueeze(0))
+
+
+# --------------------------------------------------------------------------------------------
+# Greedy question decode (QstEncoder.generate): one persistent cooperative kernel
+# --------------------------------------------------------------------------------------------
+def decode_supported(h0, lstm, word2vec, proj):
+    """Shapes pcd_decode_greedy takes (single-layer LSTM, batch <= 64, hidden a multiple of 32 up to 512, E % 4 == 0)."""
+    H = lstm.hidden_size
+    return (h0.is_cuda or N._emu_lib is not None) and lstm.num_layers == 1 and not lstm.bidirectional and lstm.bias and \
+        h0.shape[0] <= 64 and 32 <= H <= 512 and H % 32 == 0 and word2vec.embedding_dim % 4 == 0 and \
+        proj.in_features == H and proj.bias is not None and h0.dtype == torch.float32
+
+
+def decode_greedy(h0, lstm, word2vec, proj, max_length, start_token=2):
+    """tokens (B, max_length) int64 of the greedy decode that starts from `start_token` with h0 = c0 = `h0` (B, H).
+    Not differentiable (neither is the reference's argmax): parameters are read detached."""
+    lib = N.lib_for(h0)
+    B, H = h0.shape
+    V, E = word2vec.weight.shape
+    h0c = _f32c(h0)
+    ops = [_f32c(t) for t in (word2vec.weight, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)]
+    wout, bout = _f32c(proj.weight), _f32c(proj.bias)
+    tokens = torch.empty((B, max_length), dtype=torch.long, device=h0.device)
+    work = torch.empty(int(lib.pcd_decode_work_floats(B, H, V)), dtype=torch.float32, device=h0.device)
+    N.check(lib, lib.pcd_decode_greedy(max_length, B, H, E, V, start_token, *[N.ptr(t) for t in ops], N.ptr(h0c), N.ptr(h0c),
+                                       N.ptr(wout), N.ptr(bout), N.ptr(tokens), N.ptr(work), N.stream_for(h0)), "pcd_decode_greedy")
+    return tokens

@@ -456,3 +456,40 @@ def architect_lct_case(device):
     for tw_a, a in zip(arch._twins[id(ef)].arch_parameters(), before):
         assert torch.equal(tw_a.detach(), a)
     return arch
+
+
+def decode_case(device, B, H, E, V, T, seed=3):
+    """pcd_decode_greedy vs the reference's own loop (vqa_model.py:103-136) in fp64, teacher-forced with the kernel's words so
+    that one rounding-level tie cannot desynchronise the rest: every chosen word must be an argmax of the fp64 logits up to
+    fp32 rounding, and (ties being measure-zero) essentially all of them must be THE argmax."""
+    from pcd_ops import decode_greedy, decode_supported
+    g = torch.Generator().manual_seed(seed)
+    emb = torch.nn.Embedding(V, E)
+    lstm = torch.nn.LSTM(E, H, 1)
+    proj = torch.nn.Linear(H, V)
+    with torch.no_grad():
+        for p in list(emb.parameters()) + list(lstm.parameters()) + list(proj.parameters()):
+            p.copy_(torch.randn(p.shape, generator=g) * (0.5 if p.dim() > 1 else 0.1) / (p.shape[-1] ** 0.5 if p.dim() > 1 else 1.0))
+        emb.weight.mul_(E ** 0.5)
+    h0 = torch.randn(B, H, generator=g) * 0.5
+    mods = [m.to(device) for m in (emb, lstm, proj)]
+    assert decode_supported(h0.to(device), *mods[1:2], mods[0], mods[2])
+    tokens = decode_greedy(h0.to(device), mods[1], mods[0], mods[2], T, start_token=2).cpu()
+    assert tokens.shape == (B, T) and tokens.dtype == torch.long
+    assert int(tokens.min()) >= 0 and int(tokens.max()) < V
+    embd, lstmd, projd = emb.cpu().double(), lstm.cpu().double(), proj.cpu().double()
+    state = (h0.double().view(1, B, H), h0.double().view(1, B, H))
+    cur = torch.tanh(embd(torch.full((B, 1), 2, dtype=torch.long))).transpose(0, 1)
+    exact = 0
+    with torch.no_grad():
+        for t in range(T):
+            out, state = lstmd(cur, state)
+            logits = projd(torch.tanh(out.transpose(0, 1)))[:, 0]            # B x V
+            top = logits.max(dim=1)
+            mine = logits.gather(1, tokens[:, t:t + 1])[:, 0]
+            scale = logits.abs().max().item()
+            assert (top.values - mine).max().item() <= 2e-5 * scale, (t, (top.values - mine).max().item(), scale)
+            exact += int((top.indices == tokens[:, t]).sum())
+            cur = embd(tokens[:, t:t + 1]).transpose(0, 1)                   # teacher-force the kernel's word
+    assert exact >= 0.98 * B * T, (exact, B * T)
+    return exact / (B * T)

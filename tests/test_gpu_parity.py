@@ -247,6 +247,30 @@ def test_graphed_lct_step_matches_eager():
             assert_close(Lg["gamma_n"][i], Le["gamma_n"][i], 1e-3, f"gamma_n{i}")
 
 
+@pytest.mark.parametrize("B,H,E,V,T", [(64, 512, 300, 17858, 30), (5, 32, 12, 300, 7), (37, 128, 64, 1000, 12), (64, 256, 300, 129, 5)])
+def test_greedy_decode(B, H, E, V, T):
+    """Persistent greedy-decode kernel vs the reference loop in fp64 (production size first; ragged vocabulary tiles, partial
+    batches, fewer gate blocks than vocabulary tiles and the reverse)."""
+    P.decode_case(DEV, B, H, E, V, T)
+
+
+def test_generate_uses_decode_kernel():
+    """QstEncoder.generate (both packages) == its own stock-torch loop, and it goes through the native decode."""
+    import pcd_native
+    from vqa_model import QstEncoder
+    torch.manual_seed(5)
+    q = QstEncoder(700, 20, 64, 1, 64).to(DEV)
+    img = torch.randn(6, 64, device=DEV) * 0.5
+    lib = pcd_native.load_cuda()
+    n0 = lib.pcd_launch_count()
+    fast = q.generate(img)
+    assert lib.pcd_launch_count() == n0 + 1
+    q.deterministic = None            # falsy but argmax in sample(): forces the torch loop
+    q.sample = lambda prob: torch.argmax(prob, 2)
+    slow = q.generate(img)
+    assert (fast == slow).float().mean().item() >= 0.98
+
+
 def test_native_library_is_the_one_running():
     import pcd_native
     lib = pcd_native.load_cuda()
