@@ -20,7 +20,9 @@
 
 namespace pcd {
 namespace decode {
-constexpr int kT = 256, kUnits = 4, kMaxB = 64, kTileN = 128, kKC = 32, kWP = kKC + 4;
+constexpr int kT = 256, kUnits = 4, kMaxB = 64, kTileN = 128, kKC = 32, kWP = kKC + 4, kStages = 4;
+constexpr int kStageFloats = (kMaxB + kTileN) * kWP;
+PCD_HOSTDEV int u_floats(int H) { return kMaxB * (H + 4) > kStages * kStageFloats ? kMaxB * (H + 4) : kStages * kStageFloats; }
 static inline int tiles_of(int V) { return (V + kTileN - 1) / kTileN; }
 static inline bool shape_ok(int T, int B, int H, int E, int V) {
     return T > 0 && B > 0 && B <= kMaxB && H >= 32 && H <= 512 && H % 32 == 0 && E > 0 && E % 4 == 0 && V > 0;
@@ -45,8 +47,7 @@ struct Args {
     long long* tokens;    // [B][T]
     float* hbuf;          // [2][B][H]  h_t, double-buffered by step parity
     float* tbuf;          // [B][H]     tanh(h_t): the input of the vocabulary projection
-    float* cand_val;      // [B][ntiles]
-    int* cand_idx;        // [B][ntiles]
+    float2* cand;         // [B][ntiles]  (logit, index bits): one 8-byte word per row and vocabulary tile
 };
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
@@ -55,17 +56,38 @@ __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
 }
 __device__ __forceinline__ bool better(float v, int i, float best, int bi) { return v > best || (v == best && i < bi); }
 
+// [B][H] (L2: written by other SMs) -> shared memory rows of pitch H + 4, 16-byte cp.async, no commit
+__device__ __forceinline__ void stage_rows(float* Hs, const float* src, int B, int H) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, HP = H + 4;
+    for (int bb = warp; bb < B; bb += kT / 32) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(Hs + bb * HP);
+        const float* s = src + (long long)bb * H;
+        for (int k = 4 * lane; k < H; k += 128)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * k), "l"(s + k) : "memory");
+    }
+}
+
 // candidates of the previous step -> TOK[row]
 __device__ __forceinline__ void pick_words(const Args& a, int* TOK) {
     const int row = threadIdx.x >> 2, part = threadIdx.x & 3;
     float best = -INFINITY;
     int bi = INT_MAX;
-    if (row < a.B)
-        for (int k = part; k < a.ntiles; k += 4) {
-            const float v = __ldcg(a.cand_val + (long long)row * a.ntiles + k);
-            const int i = __ldcg(a.cand_idx + (long long)row * a.ntiles + k);
-            if (better(v, i, best, bi)) { best = v; bi = i; }
+    if (row < a.B) {
+        const float2* cr = a.cand + (long long)row * a.ntiles;
+        for (int k0 = part; k0 < a.ntiles; k0 += 32) {            // 8 independent loads in flight per thread
+            float2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + 4 * j;
+                v[j] = k < a.ntiles ? __ldcg(cr + k) : make_float2(-INFINITY, __int_as_float(INT_MAX));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = __float_as_int(v[j].y);
+                if (better(v[j].x, i, best, bi)) { best = v[j].x; bi = i; }
+            }
         }
+    }
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -81,9 +103,10 @@ __global__ void __launch_bounds__(kT, 1) decode_kernel(Args a) {
     const int H = a.H, E = a.E, B = a.B, HP = H + 4, EP = E + 4, H4 = H / 4, E4 = E / 4;
     float* Ws = sm;                       // [16][HP]  row q*4+u <- W_hh row q*H + u0 + u
     float* Wi = Ws + 16 * HP;             // [16][EP]  same rows of W_ih
-    float* Hs = Wi + 16 * EP;             // [64][HP]  h_{t-1} (phase A) / tanh(h_t) (phase B)
-    float* Wt = Hs + kMaxB * HP;          // [2][128][kWP] W_out tile, K chunks of 32
-    int* TOK = reinterpret_cast<int*>(Wt + 2 * kTileN * kWP);      // [64]
+    float* U = Wi + 16 * EP;              // phase A: Hs [B][HP] = h_{t-1};  phase B: kStages x ([64][kWP] | [128][kWP]) chunk ring
+    float* Hs = U;
+    int* TOK = reinterpret_cast<int*>(U + u_floats(H));            // [64]
+    float* XP = reinterpret_cast<float*>(TOK + kMaxB);             // [4 quarters][16 gate rows][64] input-projection partials
     const int tid = threadIdx.x;
     const bool gate_block = (int)blockIdx.x < H / kUnits;
     const int u0 = blockIdx.x * kUnits;
@@ -107,7 +130,6 @@ __global__ void __launch_bounds__(kT, 1) decode_kernel(Args a) {
             c = a.c0[(long long)b * H + unit];
         }
     }
-    for (int i = tid; i < (kMaxB - B) * HP; i += kT) Hs[B * HP + i] = 0.f;      // rows past the batch: never written again
     const int nk = H / kKC;
     for (int t = 0; t < a.T; ++t) {
         // ---- the word chosen at the previous step ------------------------------------------------------------------------
@@ -118,34 +140,42 @@ __global__ void __launch_bounds__(kT, 1) decode_kernel(Args a) {
         // ---- phase A: one LSTM step for this block's 4 hidden units ----------------------------------------------------------
         if (gate_block) {
             const float* hprev = t ? a.hbuf + (long long)((t - 1) & 1) * B * H : a.h0;
-            for (int i = tid; i < B * H4; i += kT) {
-                const int bb = i / H4, k4 = i - bb * H4;
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(Hs + bb * HP + 4 * k4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(hprev + (long long)bb * H + 4 * k4) : "memory");
-            }
+            stage_rows(Hs, hprev, B, H);
             asm volatile("cp.async.commit_group;" ::: "memory");
-            float acc[4] = {bsum[0], bsum[1], bsum[2], bsum[3]};
-            if (b < B) {                                  // input projection while h_{t-1} is in flight
+            // input projection while h_{t-1} is in flight: thread (b, u) takes quarter u of x_b against all 16 gate rows of
+            // the block (its ~19 float4 of the embedding row are independent loads), partial sums meet in shared memory
+            if (b < B) {
                 const float4* xr = reinterpret_cast<const float4*>(a.emb + (long long)TOK[b] * E);
+                const int kq0 = (E4 * u) >> 2, kq1 = (E4 * (u + 1)) >> 2;
+                float p[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) p[r] = 0.f;
                 if (t == 0) {                             // <start>: tanh(emb[2]) (vqa_model.py:119)
-                    for (int k4 = 0; k4 < E4; ++k4) {
+                    for (int k4 = kq0; k4 < kq1; ++k4) {
                         float4 x = __ldg(xr + k4);
                         x.x = tanhf(x.x); x.y = tanhf(x.y); x.z = tanhf(x.z); x.w = tanhf(x.w);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[q] = dot4(x, *reinterpret_cast<const float4*>(Wi + (q * 4 + u) * EP + 4 * k4), acc[q]);
+                        for (int r = 0; r < 16; ++r) p[r] = dot4(x, *reinterpret_cast<const float4*>(Wi + r * EP + 4 * k4), p[r]);
                     }
                 } else {
-#pragma unroll 15
-                    for (int k4 = 0; k4 < E4; ++k4) {
+#pragma unroll 10
+                    for (int k4 = kq0; k4 < kq1; ++k4) {
                         const float4 x = __ldg(xr + k4);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[q] = dot4(x, *reinterpret_cast<const float4*>(Wi + (q * 4 + u) * EP + 4 * k4), acc[q]);
+                        for (int r = 0; r < 16; ++r) p[r] = dot4(x, *reinterpret_cast<const float4*>(Wi + r * EP + 4 * k4), p[r]);
                     }
                 }
+#pragma unroll
+                for (int r = 0; r < 16; ++r) XP[(u * 16 + r) * kMaxB + b] = p[r];
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             if (b < B) {
+                float acc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    acc[q] = bsum[q] + ((XP[(0 * 16 + q * 4 + u) * kMaxB + b] + XP[(1 * 16 + q * 4 + u) * kMaxB + b]) +
+                                        (XP[(2 * 16 + q * 4 + u) * kMaxB + b] + XP[(3 * 16 + q * 4 + u) * kMaxB + b]));
                 const float* hr = Hs + b * HP;
 #pragma unroll 4
                 for (int k4 = 0; k4 < H4; ++k4) {
@@ -162,47 +192,53 @@ __global__ void __launch_bounds__(kT, 1) decode_kernel(Args a) {
         }
         grid.sync();
         // ---- phase B: vocabulary logits of this block's tiles, row-wise argmax candidates ----------------------------------------
-        if ((int)blockIdx.x < a.ntiles) {
-            for (int i = tid; i < B * H4; i += kT) {            // tanh(h_t) -> shared memory; joins the first W_out chunk's group
-                const int bb = i / H4, k4 = i - bb * H4;
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(Hs + bb * HP + 4 * k4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a.tbuf + (long long)bb * H + 4 * k4) : "memory");
-            }
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        // K chunks of 32: (tanh(h_t) rows | W_out tile rows) pairs through a kStages-deep cp.async ring in the U region
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            {
                 const int col0 = tile * kTileN;
                 auto issue = [&](int kc) {
-                    float* dstb = Wt + (kc & 1) * kTileN * kWP;
+                    float* sbuf = U + (kc % kStages) * kStageFloats;
+                    float* wbuf = sbuf + kMaxB * kWP;
+#pragma unroll
+                    for (int i = tid; i < kMaxB * (kKC / 4); i += kT) {
+                        const int row = i >> 3, j = i & 7;
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(sbuf + row * kWP + 4 * j);
+                        const float* src = a.tbuf + (long long)(row < B ? row : B - 1) * H + kc * kKC + 4 * j;
+                        const int nbytes = row < B ? 16 : 0;           // rows past the batch: zero fill
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+                    }
+#pragma unroll
                     for (int i = tid; i < kTileN * (kKC / 4); i += kT) {
                         const int col = i >> 3, j = i & 7;
                         const int gc = col0 + col;
-                        const unsigned dst = (unsigned)__cvta_generic_to_shared(dstb + col * kWP + 4 * j);
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(wbuf + col * kWP + 4 * j);
                         const float* src = a.w_out + (long long)(gc < a.V ? gc : a.V - 1) * H + kc * kKC + 4 * j;
                         const int nbytes = gc < a.V ? 16 : 0;          // columns past V: zero fill
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
                     }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
                 };
                 float acc[4][8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-                issue(0);
+#pragma unroll
+                for (int s = 0; s < kStages - 1; ++s) {
+                    if (s < nk) issue(s);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
                 for (int kc = 0; kc < nk; ++kc) {
-                    if (kc + 1 < nk) {
-                        issue(kc + 1);
-                        asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    } else {
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    }
-                    __syncthreads();
-                    const float* wb = Wt + (kc & 1) * kTileN * kWP;
-                    const float* sb = Hs + kc * kKC;
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
+                    __syncthreads();              // chunk kc landed for everyone; everyone is done with chunk kc - 1
+                    if (kc + kStages - 1 < nk) issue(kc + kStages - 1);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    const float* sb = U + (kc % kStages) * kStageFloats;
+                    const float* wb = sb + kMaxB * kWP;
 #pragma unroll
                     for (int k4 = 0; k4 < kKC / 4; ++k4) {
                         float4 s[4], w[8];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) s[i] = *reinterpret_cast<const float4*>(sb + (4 * ty + i) * HP + 4 * k4);
+                        for (int i = 0; i < 4; ++i) s[i] = *reinterpret_cast<const float4*>(sb + (4 * ty + i) * kWP + 4 * k4);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const float4*>(wb + (tx + 16 * j) * kWP + 4 * k4);
 #pragma unroll
@@ -210,8 +246,8 @@ __global__ void __launch_bounds__(kT, 1) decode_kernel(Args a) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) acc[i][j] = dot4(s[i], w[j], acc[i][j]);
                     }
-                    __syncthreads();          // the buffer is refilled two chunks later
                 }
+                __syncthreads();                  // ring free again (next tile's prologue / next step's h staging)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float best = -INFINITY;
@@ -232,8 +268,7 @@ __global__ void __launch_bounds__(kT, 1) decode_kernel(Args a) {
                     }
                     const int row = 4 * ty + i;
                     if (tx == 0 && row < B) {
-                        __stcg(a.cand_val + (long long)row * a.ntiles + tile, best);
-                        __stcg(a.cand_idx + (long long)row * a.ntiles + tile, bi);
+                        __stcg(a.cand + (long long)row * a.ntiles + tile, make_float2(best, __int_as_float(bi)));
                     }
                 }
             }
@@ -258,8 +293,7 @@ extern "C" int pcd_decode_greedy(int T, int B, int H, int E, int V, int start_to
     if (!decode::shape_ok(T, B, H, E, V) || start_token < 0 || start_token >= V) return PCD_ERR_UNSUPPORTED;
     if ((((uintptr_t)emb) | ((uintptr_t)w_ih) | ((uintptr_t)w_hh) | ((uintptr_t)h0) | ((uintptr_t)w_out) | ((uintptr_t)work)) & 15) return PCD_ERR_ALIGN;
     LaunchState& L = launch_state();
-    const size_t smem = ((size_t)16 * (H + 4) + (size_t)16 * (E + 4) + (size_t)decode::kMaxB * (H + 4) +
-                         (size_t)2 * decode::kTileN * decode::kWP + decode::kMaxB) * sizeof(float);
+    const size_t smem = ((size_t)16 * (H + 4) + (size_t)16 * (E + 4) + (size_t)decode::u_floats(H) + decode::kMaxB + 64 * decode::kMaxB) * sizeof(float);
     if (smem > 227 * 1024) return PCD_ERR_UNSUPPORTED;
     static int sms = 0;
     if (!sms) {
@@ -281,8 +315,7 @@ extern "C" int pcd_decode_greedy(int T, int B, int H, int E, int V, int start_to
     a.tokens = tokens;
     a.hbuf = work;
     a.tbuf = work + (size_t)2 * B * H;
-    a.cand_val = work + (size_t)3 * B * H;
-    a.cand_idx = reinterpret_cast<int*>(a.cand_val + (size_t)B * ntiles);
+    a.cand = reinterpret_cast<float2*>(work + (size_t)3 * B * H);
     void* args[] = {&a};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)decode::decode_kernel, dim3(grid), dim3(decode::kT), args, smem, (cudaStream_t)stream);
     ++L.launches;
