@@ -20,7 +20,7 @@
 
 namespace pcd {
 namespace decode {
-constexpr int kT = 256, kUnits = 4, kMaxB = 64, kTileN = 128, kKC = 32, kWP = kKC + 4, kStages = 4;
+constexpr int kT = 256, kUnits = 4, kMaxB = 64, kTileN = 128, kKC = 32, kWP = kKC + 4, kStages = 4, kPickJ = 5;
 constexpr int kStageFloats = (kMaxB + kTileN) * kWP;
 PCD_HOSTDEV int u_floats(int H) { return kMaxB * (H + 4) > kStages * kStageFloats ? kMaxB * (H + 4) : kStages * kStageFloats; }
 static inline int tiles_of(int V) { return (V + kTileN - 1) / kTileN; }
@@ -67,34 +67,44 @@ __device__ __forceinline__ void stage_rows(float* Hs, const float* src, int B, i
     }
 }
 
-// candidates of the previous step -> TOK[row]
+// candidates of the previous step -> TOK[row].  Warp w takes rows 8w .. 8w+7, lane l the tiles l, l+32, ...: the first
+// kPickJ x 8 loads of a lane are independent (one L2 round trip for up to 32 kPickJ tiles), then 8 warp reductions.
 __device__ __forceinline__ void pick_words(const Args& a, int* TOK) {
-    const int row = threadIdx.x >> 2, part = threadIdx.x & 3;
-    float best = -INFINITY;
-    int bi = INT_MAX;
-    if (row < a.B) {
-        const float2* cr = a.cand + (long long)row * a.ntiles;
-        for (int k0 = part; k0 < a.ntiles; k0 += 32) {            // 8 independent loads in flight per thread
-            float2 v[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2 cv[8][kPickJ];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = k0 + 4 * j;
-                v[j] = k < a.ntiles ? __ldcg(cr + k) : make_float2(-INFINITY, __int_as_float(INT_MAX));
-            }
+    for (int r = 0; r < 8; ++r) {
+        const int row = warp * 8 + r;
+        const float2* cr = a.cand + (long long)(row < a.B ? row : 0) * a.ntiles;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int i = __float_as_int(v[j].y);
-                if (better(v[j].x, i, best, bi)) { best = v[j].x; bi = i; }
-            }
+        for (int j = 0; j < kPickJ; ++j) {
+            const int k = lane + 32 * j;
+            cv[r][j] = (row < a.B && k < a.ntiles) ? __ldcg(cr + k) : make_float2(-INFINITY, __int_as_float(INT_MAX));
         }
     }
 #pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    for (int r = 0; r < 8; ++r) {
+        const int row = warp * 8 + r;
+        float best = -INFINITY;
+        int bi = INT_MAX;
+#pragma unroll
+        for (int j = 0; j < kPickJ; ++j) {
+            const int i = __float_as_int(cv[r][j].y);
+            if (better(cv[r][j].x, i, best, bi)) { best = cv[r][j].x; bi = i; }
+        }
+        if (row < a.B)
+            for (int k = lane + 32 * kPickJ; k < a.ntiles; k += 32) {          // only for V > 4096 kPickJ
+                const float2 c = __ldcg(a.cand + (long long)row * a.ntiles + k);
+                if (better(c.x, __float_as_int(c.y), best, bi)) { best = c.x; bi = __float_as_int(c.y); }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0 && row < a.B) TOK[row] = (bi >= 0 && bi < a.V) ? bi : 0;
     }
-    if (part == 0 && row < a.B) TOK[row] = (bi >= 0 && bi < a.V) ? bi : 0;
 }
 
 __global__ void __launch_bounds__(kT, 1) decode_kernel(Args a) {

@@ -72,6 +72,14 @@ def test_w_step_with_wgrad_overlap_matches_golden():
 
 
 # tcgen05 3xTF32 projection (nn.Linear drop-in) vs an fp64 reference: forward, dX (split-K), dW, db; ragged tiles
+@pytest.mark.parametrize("cpp,cp,C,red,rp,H,B", [(48, 48, 16, False, False, 64, 5), (64, 128, 64, True, True, 32, 7),
+                                                 (128, 256, 64, False, True, 16, 9), (48, 64, 32, True, False, 64, 1)])
+def test_cell_production_geometry_ragged_batch(cpp, cp, C, red, rp, H, B):
+    """Batches that do not divide the kernels' image groups (weight-grad jobs walk 4 images per block, source-grad / stem
+    blocks take several): the last group is partial."""
+    P.cell_vs_oracle(cpp, cp, C, red, rp, B, H, DEV, act_only=False)
+
+
 @pytest.mark.parametrize("M,K,N", [(1920, 512, 17858), (64, 512, 1000), (120, 36, 70), (256, 1024, 512), (64, 12544, 512),
                                    (64, 1000, 1000), (6, 16, 12)])
 def test_linear_3xtf32_vs_fp64(M, K, N):
