@@ -6,12 +6,12 @@
 namespace pcd {
 
 template <int C, int TH, int TW> struct KBwdB2 {
-    static constexpr int kMinBlocks = 3;
+    static constexpr int kMinBlocks = 4;      // 64 registers, 44-52 KB
     static const char* name() { return C == 4 ? "bwdB_c4" : C == 8 ? "bwdB_c8" : "bwdB_c16"; }
     static PCD_D void run(const EdgeBwdArgs& a, int x, int y, int z, float* sm) { bwdB2_body<C, TH, TW>(a, x, y, z, sm); }
 };
 template <int C, int S, int TH, int TW> struct KBwdA2 {
-    static constexpr int kMinBlocks = (C == 16 && S == 2) ? 2 : 3;
+    static constexpr int kMinBlocks = (C == 16 && S == 2) ? 2 : (C == 4 ? 4 : 3);      // c4: 64 registers, 53 KB -> 4 blocks/SM
     static const char* name() {
         return S == 1 ? (C == 4 ? "bwdA_c4_s1" : C == 8 ? "bwdA_c8_s1" : "bwdA_c16_s1") : (C == 8 ? "bwdA_c8_s2" : "bwdA_c16_s2");
     }
