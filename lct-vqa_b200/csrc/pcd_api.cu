@@ -73,14 +73,14 @@ static int stream_join(void* stream, void* aux) {
 }
 
 // ---- kernel body adaptors -----------------------------------------------------------------------------
-template <int C> struct KCombine { static constexpr int kMinBlocks = 1; static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
+template <int C> struct KCombine { static constexpr int kMinBlocks = 3; static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
 struct KNorm { static constexpr int kMinBlocks = 1; static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
 struct KStem { static constexpr int kMinBlocks = 1; static const char* name() { return "Stem"; } static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
 struct KGapF { static constexpr int kMinBlocks = 1; static const char* name() { return "GapF"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };
 struct KGapB { static constexpr int kMinBlocks = 1; static const char* name() { return "GapB"; } static PCD_D void run(const GapArgs& a, int x, int y, int, float*) { gap_bwd_body(a, x, y, a.ny); } };
 struct KShuffle { static constexpr int kMinBlocks = 1; static const char* name() { return "Shuffle"; } static PCD_D void run(const ShuffleArgs& a, int x, int y, int z, float*) { shuffle_body(a, x, y, z); } };
-template <int C> struct KNodeStats { static constexpr int kMinBlocks = 1; static const char* name() { return C == 4 ? "node_stats_c4" : C == 8 ? "node_stats_c8" : "node_stats_c16"; } static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
-struct KSourceGrad { static constexpr int kMinBlocks = 1; static const char* name() { return "SourceGrad"; } static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
+template <int C> struct KNodeStats { static constexpr int kMinBlocks = 3; static const char* name() { return C == 4 ? "node_stats_c4" : C == 8 ? "node_stats_c8" : "node_stats_c16"; } static PCD_D void run(const NodeStatsArgs& a, int x, int y, int z, float* sm) { node_stats_body<C>(a, x, y, z, sm); } };
+struct KSourceGrad { static constexpr int kMinBlocks = 4; static const char* name() { return "SourceGrad"; } static PCD_D void run(const SourceGradArgs& a, int x, int y, int z, float*) { source_grad_body(a, x, y, z); } };
 struct KArchGrads { static constexpr int kMinBlocks = 1; static const char* name() { return "ArchGrads"; } static PCD_D void run(const ArchGradArgs& a, int, int, int, float* sm) { arch_grads_body(a, sm); } };
 struct KBnBwdStats { static constexpr int kMinBlocks = 1; static const char* name() { return "BnBwdStats"; } static PCD_D void run(const BnBwdStatArgs& a, int x, int y, int z, float* sm) { bn_bwd_stats_body(a, x, y, z, sm); } };
 struct KStemBwd { static constexpr int kMinBlocks = 1; static const char* name() { return "StemBwd"; } static PCD_D void run(const StemBwdArgs& a, int x, int, int, float* sm) { stem_bwd_body(a, x, a.nblocks_launch, sm); } };
@@ -137,7 +137,8 @@ static int run_combine(int B, int c, int Ho, int Wo, float eps, float mom, float
     a.B = B; a.Ho = Ho; a.Wo = Wo; a.eps = eps; a.momentum = mom; a.nin = n; a.update_running = 1;
     a.out = out; a.out_ns = out_ns;
     for (int i = 0; i < n; ++i) a.e[i] = edges[i];
-    const int chunks = (Ho * Wo + kCombinePx - 1) / kCombinePx;
+    a.px_per_block = combine_px(c);
+    const int chunks = (Ho * Wo + a.px_per_block - 1) / a.px_per_block;
     PCD_DISPATCH_C(c, PCD_TRY((launch<KCombine<CC>, CombineArgs>(a, chunks, B, 1, combine_smem_floats(CC), stream))));
     return PCD_OK;
 }

@@ -184,6 +184,40 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
     const bool vec = (HW % 4 == 0) && (p0 % 4 == 0) && ((((uintptr_t)a.out) | ((uintptr_t)a.x)) & 15) == 0 &&
                      a.out_ns % 4 == 0 && a.x_ns % 4 == 0 && (!a.g0 || (((((uintptr_t)a.g0) & 15) == 0) && a.g0_ns % 4 == 0));
     const int tpp = npx / 4;          // float4 tasks per plane chunk
+    bool all_merged = true, all_s1 = true;
+    for (int k = 0; k < a.nedges; ++k) {
+        all_merged = all_merged && a.e[k].merged;
+        all_s1 = all_s1 && a.e[k].stride == 1;
+    }
+    if (ch < c && vec && all_merged) {
+        // production path: every load of a task (2 per edge + mask + initial grad) is issued before the first use
+        PCD_FOR(tt, nimg * tpp) {
+            const int n = n0 + tt / tpp, i4 = tt % tpp;
+            if (n >= a.B) continue;
+            const int p = p0 + i4 * 4;
+            const long long off = ((long long)n * c + ch) * HW + p;
+            F4 m[kMaxSrcEdges], q4[kMaxSrcEdges];
+#pragma unroll
+            for (int k = 0; k < kMaxSrcEdges; ++k)
+                if (k < a.nedges) {
+                    m[k] = *reinterpret_cast<const F4*>(a.e[k].pd + off);
+                    q4[k] = *reinterpret_cast<const F4*>(a.e[k].pd + off + pslot);
+                }
+            const F4 xv = *reinterpret_cast<const F4*>(a.x + (long long)n * a.x_ns + (long long)ch * HW + p);
+            F4 v = {0.f, 0.f, 0.f, 0.f};
+            if (a.g0) v = *reinterpret_cast<const F4*>(a.g0 + (long long)n * a.g0_ns + (long long)ch * HW + p);
+#pragma unroll
+            for (int k = 0; k < kMaxSrcEdges; ++k)
+                if (k < a.nedges) {
+                    v.x += (xv.x > 0.f ? m[k].x : 0.f) + q4[k].x;
+                    v.y += (xv.y > 0.f ? m[k].y : 0.f) + q4[k].y;
+                    v.z += (xv.z > 0.f ? m[k].z : 0.f) + q4[k].z;
+                    v.w += (xv.w > 0.f ? m[k].w : 0.f) + q4[k].w;
+                }
+            *reinterpret_cast<F4*>(a.out + (long long)n * a.out_ns + (long long)ch * HW + p) = v;
+        }
+        return;
+    }
     if (ch < c && vec) {
         PCD_FOR(tt, nimg * tpp) {
             const int n = n0 + tt / tpp, i4 = tt % tpp;
@@ -228,6 +262,29 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
     bool vecb = vec && ch >= c && a.Ws % 4 == 0;
     for (int k = 0; k < a.nedges; ++k)
         vecb = vecb && ((((uintptr_t)a.e[k].dn) & 15) == 0) && a.e[k].dn_ns % 4 == 0 && (a.e[k].stride == 1 || a.Ws % 8 == 0);
+    if (vecb && all_s1) {
+        // bypass channels, every consumer at stride 1: one load per edge, all in flight together
+        const int q = ch / c, j = ch - q * c;
+        PCD_FOR(tt, nimg * tpp) {
+            const int n = n0 + tt / tpp, i4 = tt % tpp;
+            if (n >= a.B) continue;
+            const int p = p0 + i4 * 4;
+            F4 d[kMaxSrcEdges];
+#pragma unroll
+            for (int k = 0; k < kMaxSrcEdges; ++k)
+                if (k < a.nedges) d[k] = *reinterpret_cast<const F4*>(a.e[k].dn + (long long)n * a.e[k].dn_ns + (long long)(4 * j + q) * HW + p);
+            F4 v = {0.f, 0.f, 0.f, 0.f};
+            if (a.g0) v = *reinterpret_cast<const F4*>(a.g0 + (long long)n * a.g0_ns + (long long)ch * HW + p);
+#pragma unroll
+            for (int k = 0; k < kMaxSrcEdges; ++k)
+                if (k < a.nedges) {
+                    const float beta = a.e[k].beta ? a.e[k].beta[0] : 1.f;
+                    v.x = fmaf(beta, d[k].x, v.x); v.y = fmaf(beta, d[k].y, v.y); v.z = fmaf(beta, d[k].z, v.z); v.w = fmaf(beta, d[k].w, v.w);
+                }
+            *reinterpret_cast<F4*>(a.out + (long long)n * a.out_ns + (long long)ch * HW + p) = v;
+        }
+        return;
+    }
     if (vecb) {
         const int q = ch / c, j = ch - q * c;
         PCD_FOR(tt, nimg * tpp) {

@@ -31,14 +31,17 @@ struct CombineArgs {
     int B, Ho, Wo;
     float eps, momentum;
     int nin, update_running;
+    int px_per_block;      // pixels of one image per block (multiple of 4)
     float* out;            // node tensor (B, C, Ho, Wo) view
     long long out_ns;
     EdgeC e[kMaxNodeIn];
 };
 
-constexpr int kCombinePx = 1024;
+// pixels per block: one float4 strip per thread and channel where the image is large enough to still fill the GPU
+// (a node of cell 2/3 is only 64 images x 256 pixels: 64-pixel chunks give 256 blocks instead of 64)
+PCD_HOSTDEV int combine_px(int C) { return 1024 / C; }
 
-PCD_HOSTDEV size_t combine_smem_floats(int C) { return (size_t)kMaxNodeIn * 8 * C + 16; }
+PCD_HOSTDEV size_t combine_smem_floats(int C) { return (size_t)kMaxNodeIn * (8 + 7) * C + 16; }
 
 // coefficient rows per edge: 0 P1, 1 P2, 2 B3, 3 B5, 4 D3, 5 D5, 6 F (stride 2) or identity (stride 1), 7 shift
 template <int C>
@@ -46,34 +49,41 @@ PCD_HD void combine_body(const CombineArgs& a, int bx, int n, float* smem) {
     float* COEF = smem;
     const double cnt = (double)a.B * a.Ho * a.Wo;
     const int HW = a.Ho * a.Wo;
-    PCD_FOR(i, a.nin * C) {
-        const int ei = i / C, j = i - ei * C;
+    // one thread per (edge, BN, channel): the fp64 statistics loads of all coefficients are in flight together
+    float* MEAN = COEF + kMaxNodeIn * 8 * C;
+    PCD_FOR(i, a.nin * 7 * C) {
+        const int ei = i / (7 * C), r = i - ei * 7 * C, k = r / C, j = r - k * C;
         const EdgeC& e = a.e[ei];
         const float beta = e.beta ? e.beta[0] : 1.f;
         const int s = e.stride;
-        const int bns[6] = {bn_p1(), bn_p2(), bn_unit(s, 1), bn_unit(s, 3), bn_unit(s, 4), bn_unit(s, 5)};
-        const int prim[6] = {1, 2, 4, 5, 6, 7};
-        float shift = 0.f;
         float* co = COEF + ei * 8 * C;
-        for (int k = 0; k < 6; ++k) {
-            BnC b = bn_consts(e.stats, C, bns[k], j, cnt, a.eps);
-            const float sc = beta * e.alpha[prim[k]] * b.rstd;
-            co[k * C + j] = sc;
-            shift -= sc * b.mean;
-        }
-        if (s == 2) {
+        if (k < 6) {
+            const int bn = k == 0 ? bn_p1() : k == 1 ? bn_p2() : bn_unit(s, k == 2 ? 1 : k + 0);
+            const int prim = k == 0 ? 1 : k == 1 ? 2 : k + 2;
+            BnC b = bn_consts(e.stats, C, bn, j, cnt, a.eps);
+            co[k * C + j] = beta * e.alpha[prim] * b.rstd;
+            MEAN[(ei * 7 + k) * C + j] = b.mean;
+        } else if (s == 2) {
             BnC b = bn_consts(e.stats, C, bn_f(), j, cnt, a.eps);
-            const float sc = beta * e.alpha[3] * b.rstd;
-            co[6 * C + j] = sc;
-            shift -= sc * b.mean;
+            co[6 * C + j] = beta * e.alpha[3] * b.rstd;
+            MEAN[(ei * 7 + 6) * C + j] = b.mean;
         } else {
             co[6 * C + j] = beta * e.alpha[3];
+            MEAN[(ei * 7 + 6) * C + j] = 0.f;
         }
-        co[7 * C + j] = shift;
     }
     PCD_SYNC();
-    const int p0 = bx * kCombinePx;
-    const int npx = (HW - p0) < kCombinePx ? (HW - p0) : kCombinePx;
+    PCD_FOR(i, a.nin * C) {
+        const int ei = i / C, j = i - ei * C;
+        const float* co = COEF + ei * 8 * C;
+        float shift = 0.f;
+        for (int k = 0; k < 6; ++k) shift -= co[k * C + j] * MEAN[(ei * 7 + k) * C + j];
+        if (a.e[ei].stride == 2) shift -= co[6 * C + j] * MEAN[(ei * 7 + 6) * C + j];
+        COEF[ei * 8 * C + 7 * C + j] = shift;
+    }
+    PCD_SYNC();
+    const int p0 = bx * a.px_per_block;
+    const int npx = (HW - p0) < a.px_per_block ? (HW - p0) : a.px_per_block;
     const int nstrip = (npx + 3) / 4;
     const long long nslot = (long long)a.B * C * HW;
     bool vec = (HW % 4 == 0) && ((((uintptr_t)a.out) & 15) == 0) && (a.out_ns % 4 == 0);
