@@ -73,7 +73,7 @@ static int stream_join(void* stream, void* aux) {
 }
 
 // ---- kernel body adaptors -----------------------------------------------------------------------------
-template <int C> struct KCombine { static constexpr int kMinBlocks = 3; static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
+template <int C> struct KCombine { static constexpr int kMinBlocks = 2; static const char* name() { return C == 4 ? "combine_c4" : C == 8 ? "combine_c8" : "combine_c16"; } static PCD_D void run(const CombineArgs& a, int x, int y, int, float* sm) { combine_body<C>(a, x, y, sm); } };
 struct KNorm { static constexpr int kMinBlocks = 1; static const char* name() { return "Norm"; } static PCD_D void run(const NormArgs& a, int x, int y, int z, float*) { norm_body(a, x, y, z); } };
 struct KStem { static constexpr int kMinBlocks = 1; static const char* name() { return "Stem"; } static PCD_D void run(const StemArgs& a, int x, int y, int, float* sm) { stem_conv_body(a, x, y, sm); } };
 struct KGapF { static constexpr int kMinBlocks = 1; static const char* name() { return "GapF"; } static PCD_D void run(const GapArgs& a, int x, int, int, float*) { gap_fwd_body(a, x); } };

@@ -99,35 +99,58 @@ PCD_HD void combine_body(const CombineArgs& a, int bx, int n, float* smem) {
             for (int q = 0; q < 3; ++q)
 #pragma unroll
                 for (int t = 0; t < 4; ++t) by[q][t] = 0.f;
+            // stride-1 edges: the 10 float4 loads of edge ei + 1 are issued before the arithmetic of edge ei (the small
+            // cells have too few threads in flight to hide the latency otherwise)
+            const int slots[6] = {slot_p1(), slot_p2(), slot_z(1), slot_z(3), slot_z(4), slot_z(5)};
+            F4 cz[6], cx[4], nz[6], nx[4];
+            auto issue = [&](int ei, F4* z, F4* x) {
+                const EdgeC& e = a.e[ei];
+                const float* sv = e.saved + ((long long)n * C + j) * HW + p;
+                const float* xb = e.x + (long long)n * e.x_ns;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) z[k] = *reinterpret_cast<const F4*>(sv + slots[k] * nslot);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x[q] = *reinterpret_cast<const F4*>(xb + (long long)(q * C + j) * HW + p);
+            };
+            if (a.e[0].stride == 1) issue(0, nz, nx);
             for (int ei = 0; ei < a.nin; ++ei) {
                 const EdgeC& e = a.e[ei];
                 const float* co = COEF + ei * 8 * C;
                 const float beta = e.beta ? e.beta[0] : 1.f;
-                const float* sv = e.saved + ((long long)n * C + j) * HW + p;
-                const float* xb = e.x + (long long)n * e.x_ns;
-                const int slots[6] = {slot_p1(), slot_p2(), slot_z(1), slot_z(3), slot_z(4), slot_z(5)};
                 float acc[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) acc[t] = co[7 * C + j];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const F4 v = *reinterpret_cast<const F4*>(sv + slots[k] * nslot);
-                    const float c = co[k * C + j];
-                    acc[0] = fmaf(c, v.x, acc[0]); acc[1] = fmaf(c, v.y, acc[1]);
-                    acc[2] = fmaf(c, v.z, acc[2]); acc[3] = fmaf(c, v.w, acc[3]);
-                }
                 const float c6 = co[6 * C + j];
                 if (e.stride == 1) {
-                    const F4 v = *reinterpret_cast<const F4*>(xb + (long long)j * HW + p);
-                    acc[0] = fmaf(c6, v.x, acc[0]); acc[1] = fmaf(c6, v.y, acc[1]);
-                    acc[2] = fmaf(c6, v.z, acc[2]); acc[3] = fmaf(c6, v.w, acc[3]);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) cz[k] = nz[k];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cx[q] = nx[q];
+                    if (ei + 1 < a.nin && a.e[ei + 1].stride == 1) issue(ei + 1, nz, nx);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const float c = co[k * C + j];
+                        acc[0] = fmaf(c, cz[k].x, acc[0]); acc[1] = fmaf(c, cz[k].y, acc[1]);
+                        acc[2] = fmaf(c, cz[k].z, acc[2]); acc[3] = fmaf(c, cz[k].w, acc[3]);
+                    }
+                    acc[0] = fmaf(c6, cx[0].x, acc[0]); acc[1] = fmaf(c6, cx[0].y, acc[1]);
+                    acc[2] = fmaf(c6, cx[0].z, acc[2]); acc[3] = fmaf(c6, cx[0].w, acc[3]);
 #pragma unroll
                     for (int q = 1; q < 4; ++q) {
-                        const F4 b = *reinterpret_cast<const F4*>(xb + (long long)(q * C + j) * HW + p);
-                        by[q - 1][0] = fmaf(beta, b.x, by[q - 1][0]); by[q - 1][1] = fmaf(beta, b.y, by[q - 1][1]);
-                        by[q - 1][2] = fmaf(beta, b.z, by[q - 1][2]); by[q - 1][3] = fmaf(beta, b.w, by[q - 1][3]);
+                        by[q - 1][0] = fmaf(beta, cx[q].x, by[q - 1][0]); by[q - 1][1] = fmaf(beta, cx[q].y, by[q - 1][1]);
+                        by[q - 1][2] = fmaf(beta, cx[q].z, by[q - 1][2]); by[q - 1][3] = fmaf(beta, cx[q].w, by[q - 1][3]);
                     }
                 } else {
+                    if (ei + 1 < a.nin && a.e[ei + 1].stride == 1) issue(ei + 1, nz, nx);
+                    const float* sv = e.saved + ((long long)n * C + j) * HW + p;
+                    const float* xb = e.x + (long long)n * e.x_ns;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const F4 v = *reinterpret_cast<const F4*>(sv + slots[k] * nslot);
+                        const float c = co[k * C + j];
+                        acc[0] = fmaf(c, v.x, acc[0]); acc[1] = fmaf(c, v.y, acc[1]);
+                        acc[2] = fmaf(c, v.z, acc[2]); acc[3] = fmaf(c, v.w, acc[3]);
+                    }
                     const F4 v = *reinterpret_cast<const F4*>(sv + slot_f() * nslot);
                     acc[0] = fmaf(c6, v.x, acc[0]); acc[1] = fmaf(c6, v.y, acc[1]);
                     acc[2] = fmaf(c6, v.z, acc[2]); acc[3] = fmaf(c6, v.w, acc[3]);
