@@ -134,6 +134,24 @@ PCD_HD void red4(float* p, float a, float b, float c, float d) {
 #endif
 }
 
+// 16-byte global -> shared copy that does not occupy a register (cp.async; zero fill when !valid); cp16_wait() makes this
+// thread's copies visible to it (a barrier then publishes them to the block)
+PCD_HD void cp16(float* dst, const float* src, bool valid) {
+#if PCD_CUDA
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int nbytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+#else
+    if (valid) { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3]; }
+    else { dst[0] = dst[1] = dst[2] = dst[3] = 0.f; }
+#endif
+}
+PCD_HD void cp16_wait() {
+#if PCD_CUDA
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // Tile rows that span the full image width W (the compile-time-tile kernels): dst[C][ROWS][W + 8] <- f(ch, src row),
 // image rows gy0 .. gy0 + ROWS - 1 (zero outside the image); the two 4-float column halos are zero padding.
 template <int C, int ROWS, int W, class F>

@@ -509,30 +509,38 @@ PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, int n0, int n1
         const int oy0 = tile * TH;
         PCD_SYNC();                               // constants ready / previous tile's readers are done
         // ---- tiles: unit input (haloed), saved depthwise output, dz ----------------------------------------
+        // the input tile and the saved depthwise output go global -> shared without passing through registers (cp.async),
+        // in flight while dz is formed from its own (register) loads; the input's ReLU / BN+ReLU is applied in place after
         const float* src = BNIN ? e.saved + slot_z(u - 1) * nslot + (long long)n * C * HW : e.x + (long long)n * e.x_ns;
         for_tasks<C * IH * (XW / 4)>([&](int i) {
             const int c4 = i % (XW / 4), r = (i / (XW / 4)) % IH, ch = i / ((XW / 4) * IH);
             const int gy = SI * oy0 - 4 + r, gx = 4 * c4 - 4;
-            F4 v = {0.f, 0.f, 0.f, 0.f};
+            const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+            cp16(IN + (size_t)i * 4, ok ? src + ch * scs + (long long)gy * W + gx : src, ok);
+        });
+        const float* tsl = e.saved + slot_t(u) * nslot + (long long)n * C * HW + (long long)oy0 * TW;
+        for_tasks<C * NPIX / 4>([&](int i) {
+            const int p4 = i % (NPIX / 4), ch = i / (NPIX / 4);
+            cp16(T + (size_t)i * 4, tsl + (long long)ch * HW + 4 * p4, true);
+        });
+        const float* dy_img = isA ? e.ga + which * nslot + (long long)n * C * HW : e.dn + (long long)n * e.dn_ns;
+        dz_rows<C, TH, TW>(DZ, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)n * C * HW, HW, COEF, oy0, a.Ho);
+        cp16_wait();
+        PCD_SYNC();
+        for_tasks<C * IH * (XW / 4)>([&](int i) {
+            const int c4 = i % (XW / 4), r = (i / (XW / 4)) % IH, ch = i / ((XW / 4) * IH);
+            const int gy = SI * oy0 - 4 + r, gx = 4 * c4 - 4;
             if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                v = ld4(src + ch * scs + (long long)gy * W + gx);
+                F4 v = ld4(IN + (size_t)i * 4);
                 if (BNIN) {
                     const float m = BNA[2 * ch], r_ = BNA[2 * ch + 1];
                     v.x = relu((v.x - m) * r_); v.y = relu((v.y - m) * r_); v.z = relu((v.z - m) * r_); v.w = relu((v.w - m) * r_);
                 } else {
                     v.x = relu(v.x); v.y = relu(v.y); v.z = relu(v.z); v.w = relu(v.w);
                 }
+                *reinterpret_cast<F4*>(IN + (size_t)i * 4) = v;
             }
-            *reinterpret_cast<F4*>(IN + (size_t)i * 4) = v;
         });
-        const float* tsl = e.saved + slot_t(u) * nslot + (long long)n * C * HW + (long long)oy0 * TW;
-        for_tasks<C * NPIX / 4>([&](int i) {
-            const int p4 = i % (NPIX / 4), ch = i / (NPIX / 4);
-            *reinterpret_cast<F4*>(T + (size_t)i * 4) = ld4(tsl + (long long)ch * HW + 4 * p4);
-        });
-        const float* dy_img = isA ? e.ga + which * nslot + (long long)n * C * HW : e.dn + (long long)n * e.dn_ns;
-        dz_rows<C, TH, TW>(DZ, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)n * C * HW, HW, COEF, oy0, a.Ho);
-        PCD_SYNC();
         // ---- dt on the centre; pointwise weight-grad partials ---------------------------------------------------
         dt_rows<C, TH, TW, TW, 0>(DT, DZ, WT, oy0, a.Ho);
         PCD_EACH(task) {
