@@ -37,6 +37,31 @@ PCD_HD void dz_rows(float* DZ, const float* PCD_RESTRICT dy_img, long long dy_cs
     });
 }
 
+// the same in two steps for tiles whose rows are all inside the image: raw dy -> DZ and raw z -> ZR with cp.async
+// (dz_stage; no registers, joins the caller's other copies), then DZ = BN-backward(DZ, ZR) in place (dz_finish)
+template <int C, int RH, int TW>
+PCD_HD void dz_stage(float* DZ, float* ZR, const float* PCD_RESTRICT dy_img, long long dy_cs, int dy_chm,
+                     const float* PCD_RESTRICT z_img, long long HW, int oyf) {
+    constexpr int W4 = TW / 4;
+    for_tasks<C * RH * W4>([&](int i) {
+        const int x4 = i % W4, r = (i / W4) % RH, co = i / (W4 * RH);
+        const long long off = (long long)(oyf + r) * TW + 4 * x4;
+        cp16(DZ + (size_t)i * 4, dy_img + (long long)(co * dy_chm) * dy_cs + off, true);
+        cp16(ZR + (size_t)i * 4, z_img + (long long)co * HW + off, true);
+    });
+}
+template <int C, int RH, int TW>
+PCD_HD void dz_finish(float* DZ, const float* ZR, const float* COEF) {
+    constexpr int W4 = TW / 4;
+    for_tasks<C * RH * W4>([&](int i) {
+        const int co = i / (W4 * RH);
+        const F4 dy = ld4(DZ + (size_t)i * 4), zz = ld4(ZR + (size_t)i * 4);
+        const float c0 = COEF[4 * co], ca = COEF[4 * co + 1], cm = COEF[4 * co + 2], c1 = COEF[4 * co + 3];
+        st4(DZ + (size_t)i * 4, c0 * (dy.x - ca - (zz.x - cm) * c1), c0 * (dy.y - ca - (zz.y - cm) * c1),
+            c0 * (dy.z - ca - (zz.z - cm) * c1), c0 * (dy.w - ca - (zz.w - cm) * c1));
+    });
+}
+
 // DT[ci][r][OFF + x] = sum_co WT[ci][co] * DZ[co][r][x]   (pitch P; rows outside the image are written as zeros)
 template <int C, int RH, int TW, int P, int OFF>
 PCD_HD void dt_rows(float* DT, const float* DZ, const float* WT, int oyf, int Ho) {
@@ -510,7 +535,8 @@ PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, int n0, int n1
         PCD_SYNC();                               // constants ready / previous tile's readers are done
         // ---- tiles: unit input (haloed), saved depthwise output, dz ----------------------------------------
         // the input tile and the saved depthwise output go global -> shared without passing through registers (cp.async),
-        // in flight while dz is formed from its own (register) loads; the input's ReLU / BN+ReLU is applied in place after
+        // like the raw dy / z rows (staged in DZ / DT): every load of the tile is in flight at once; the input's ReLU / BN+ReLU
+        // and the BN-backward that turns (dy, z) into dz are applied in place afterwards
         const float* src = BNIN ? e.saved + slot_z(u - 1) * nslot + (long long)n * C * HW : e.x + (long long)n * e.x_ns;
         for_tasks<C * IH * (XW / 4)>([&](int i) {
             const int c4 = i % (XW / 4), r = (i / (XW / 4)) % IH, ch = i / ((XW / 4) * IH);
@@ -524,9 +550,10 @@ PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, int n0, int n1
             cp16(T + (size_t)i * 4, tsl + (long long)ch * HW + 4 * p4, true);
         });
         const float* dy_img = isA ? e.ga + which * nslot + (long long)n * C * HW : e.dn + (long long)n * e.dn_ns;
-        dz_rows<C, TH, TW>(DZ, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)n * C * HW, HW, COEF, oy0, a.Ho);
+        dz_stage<C, TH, TW>(DZ, DT, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)n * C * HW, HW, oy0);
         cp16_wait();
         PCD_SYNC();
+        dz_finish<C, TH, TW>(DZ, DT, COEF);
         for_tasks<C * IH * (XW / 4)>([&](int i) {
             const int c4 = i % (XW / 4), r = (i / (XW / 4)) % IH, ch = i / ((XW / 4) * IH);
             const int gy = SI * oy0 - 4 + r, gx = 4 * c4 - 4;
@@ -541,6 +568,7 @@ PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, int n0, int n1
                 *reinterpret_cast<F4*>(IN + (size_t)i * 4) = v;
             }
         });
+        PCD_SYNC();                               // dz complete, the raw z in DT consumed
         // ---- dt on the centre; pointwise weight-grad partials ---------------------------------------------------
         dt_rows<C, TH, TW, TW, 0>(DT, DZ, WT, oy0, a.Ho);
         PCD_EACH(task) {
