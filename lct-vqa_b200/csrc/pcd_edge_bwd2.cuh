@@ -37,28 +37,33 @@ PCD_HD void dz_rows(float* DZ, const float* PCD_RESTRICT dy_img, long long dy_cs
     });
 }
 
-// the same in two steps for tiles whose rows are all inside the image: raw dy -> DZ and raw z -> ZR with cp.async
-// (dz_stage; no registers, joins the caller's other copies), then DZ = BN-backward(DZ, ZR) in place (dz_finish)
+// the same in two steps: raw dy -> DZ and raw z -> ZR with cp.async (dz_stage: no registers, needs no coefficient, so it
+// can be issued before the BN constants are even computed), then DZ = BN-backward(DZ, ZR) in place (dz_finish)
 template <int C, int RH, int TW>
 PCD_HD void dz_stage(float* DZ, float* ZR, const float* PCD_RESTRICT dy_img, long long dy_cs, int dy_chm,
-                     const float* PCD_RESTRICT z_img, long long HW, int oyf) {
+                     const float* PCD_RESTRICT z_img, long long HW, int oyf, int Ho) {
     constexpr int W4 = TW / 4;
     for_tasks<C * RH * W4>([&](int i) {
         const int x4 = i % W4, r = (i / W4) % RH, co = i / (W4 * RH);
-        const long long off = (long long)(oyf + r) * TW + 4 * x4;
-        cp16(DZ + (size_t)i * 4, dy_img + (long long)(co * dy_chm) * dy_cs + off, true);
-        cp16(ZR + (size_t)i * 4, z_img + (long long)co * HW + off, true);
+        const int oy = oyf + r;
+        const bool ok = oy >= 0 && oy < Ho;
+        const long long off = ok ? (long long)oy * TW + 4 * x4 : 0;
+        cp16(DZ + (size_t)i * 4, dy_img + (long long)(co * dy_chm) * dy_cs + off, ok);
+        cp16(ZR + (size_t)i * 4, z_img + (long long)co * HW + off, ok);
     });
 }
 template <int C, int RH, int TW>
-PCD_HD void dz_finish(float* DZ, const float* ZR, const float* COEF) {
+PCD_HD void dz_finish(float* DZ, const float* ZR, const float* COEF, int oyf, int Ho) {
     constexpr int W4 = TW / 4;
     for_tasks<C * RH * W4>([&](int i) {
-        const int co = i / (W4 * RH);
-        const F4 dy = ld4(DZ + (size_t)i * 4), zz = ld4(ZR + (size_t)i * 4);
-        const float c0 = COEF[4 * co], ca = COEF[4 * co + 1], cm = COEF[4 * co + 2], c1 = COEF[4 * co + 3];
-        st4(DZ + (size_t)i * 4, c0 * (dy.x - ca - (zz.x - cm) * c1), c0 * (dy.y - ca - (zz.y - cm) * c1),
-            c0 * (dy.z - ca - (zz.z - cm) * c1), c0 * (dy.w - ca - (zz.w - cm) * c1));
+        const int r = (i / W4) % RH, co = i / (W4 * RH);
+        const int oy = oyf + r;
+        if (oy >= 0 && oy < Ho) {           // rows outside the image stay the zeros the copy wrote
+            const F4 dy = ld4(DZ + (size_t)i * 4), zz = ld4(ZR + (size_t)i * 4);
+            const float c0 = COEF[4 * co], ca = COEF[4 * co + 1], cm = COEF[4 * co + 2], c1 = COEF[4 * co + 3];
+            st4(DZ + (size_t)i * 4, c0 * (dy.x - ca - (zz.x - cm) * c1), c0 * (dy.y - ca - (zz.y - cm) * c1),
+                c0 * (dy.z - ca - (zz.z - cm) * c1), c0 * (dy.w - ca - (zz.w - cm) * c1));
+        }
     });
 }
 
@@ -138,6 +143,10 @@ PCD_HD void bwdB2_data_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
     const float kappa = beta * e.alpha[half ? 5 : 4];
     const float* w_dw = e.par + edge_dw_off(C, S, uB);
     const float* w_pw = e.par + edge_pw_off(C, S, uB);
+    // the raw dN / zB rows start their way into shared memory (DZ / the DT area) before the BN constants are derived
+    const float* zA = e.saved + slot_z(uA) * nslot + (long long)g.n * C * HW;
+    const float* zB = e.saved + slot_z(uB) * nslot + (long long)g.n * C * HW;
+    dz_stage<C, RH, TW>(DZ, DT, e.dn + (long long)g.n * e.dn_ns, HW, 4, zB, HW, g.oy0 - PAD, a.Ho);
     PCD_FOR(j, C) {
         const int bnB = bn_unit(S, uB);
         edge_coef(COEF, j, dz_consts(e.stats, C, bnB, j, cnt, a.eps, e.bstats[bs_s0() * C + j], e.bstats[bs_sz(bnB) * C + j], kappa));
@@ -145,12 +154,11 @@ PCD_HD void bwdB2_data_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
         BNA[2 * j] = b.mean; BNA[2 * j + 1] = b.rstd;
     }
     PCD_FOR(i, C * C) WT[(i % C) * C + i / C] = w_pw[i];
+    cp16_wait();
     PCD_SYNC();
-    const float* zA = e.saved + slot_z(uA) * nslot + (long long)g.n * C * HW;
-    const float* zB = e.saved + slot_z(uB) * nslot + (long long)g.n * C * HW;
-    dz_rows<C, RH, TW>(DZ, e.dn + (long long)g.n * e.dn_ns, HW, 4, zB, HW, COEF, g.oy0 - PAD, a.Ho);
+    dz_finish<C, RH, TW>(DZ, DT, COEF, g.oy0 - PAD, a.Ho);
+    PCD_SYNC();                                     // raw zB consumed: DT can be rewritten
     zero_col_halo<C * RH, TW, IW>(DT);
-    PCD_SYNC();
     dt_rows<C, RH, TW, IW, 4>(DT, DZ, WT, g.oy0 - PAD, a.Ho);
     PCD_SYNC();
     float* ga = e.ga + half * nslot;
@@ -225,6 +233,9 @@ PCD_HD void bwdA2_conv_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
     const float* w_pw = e.par + edge_pw_off(C, S, u);
     const bool isA = (u == 0 || u == 2);
     const int which = (u == 2) ? 1 : 0;
+    // the raw dy / z rows start their way into shared memory (DZ / the DT area) before the BN constants are derived
+    const float* dy_img = isA ? e.ga + which * nslot + (long long)g.n * C * HW : e.dn + (long long)g.n * e.dn_ns;
+    dz_stage<C, RH, TW>(DZ, DT, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)g.n * C * HW, HW, g.oy0 - HY, a.Ho);
     PCD_FOR(j, C) {
         const int bn = bn_unit(S, u);
         if (isA)
@@ -235,12 +246,11 @@ PCD_HD void bwdA2_conv_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
                                          beta * e.alpha[u == 4 ? 6 : 7]));
     }
     PCD_FOR(i, C * C) WT[(i % C) * C + i / C] = w_pw[i];
+    cp16_wait();
     PCD_SYNC();
-    const float* dy_img = isA ? e.ga + which * nslot + (long long)g.n * C * HW : e.dn + (long long)g.n * e.dn_ns;
-    dz_rows<C, RH, TW>(DZ, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)g.n * C * HW, HW, COEF,
-                       g.oy0 - HY, a.Ho);
+    dz_finish<C, RH, TW>(DZ, DT, COEF, g.oy0 - HY, a.Ho);
+    PCD_SYNC();                                     // raw z consumed: DT can be rewritten
     zero_col_halo<C * RH, TW, IW>(DT);
-    PCD_SYNC();
     dt_rows<C, RH, TW, IW, 4>(DT, DZ, WT, g.oy0 - HY, a.Ho);
     PCD_SYNC();
     // v3 layout of the partial input grads: slot 0 accumulates every pre-mask partial (A3 A5 D3 D5 FR), slot 1 the two
@@ -550,10 +560,10 @@ PCD_HD void wgrad2_unit_job(const EdgeBwdArgs& a, const EdgeG& e, int n0, int n1
             cp16(T + (size_t)i * 4, tsl + (long long)ch * HW + 4 * p4, true);
         });
         const float* dy_img = isA ? e.ga + which * nslot + (long long)n * C * HW : e.dn + (long long)n * e.dn_ns;
-        dz_stage<C, TH, TW>(DZ, DT, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)n * C * HW, HW, oy0);
+        dz_stage<C, TH, TW>(DZ, DT, dy_img, HW, isA ? 1 : 4, e.saved + slot_z(u) * nslot + (long long)n * C * HW, HW, oy0, a.Ho);
         cp16_wait();
         PCD_SYNC();
-        dz_finish<C, TH, TW>(DZ, DT, COEF);
+        dz_finish<C, TH, TW>(DZ, DT, COEF, oy0, a.Ho);
         for_tasks<C * IH * (XW / 4)>([&](int i) {
             const int c4 = i % (XW / 4), r = (i / (XW / 4)) % IH, ch = i / ((XW / 4) * IH);
             const int gy = SI * oy0 - 4 + r, gx = 4 * c4 - 4;
