@@ -174,6 +174,35 @@ PCD_HD void load_rows_full(float* dst, const float* PCD_RESTRICT src, long long 
     });
 }
 
+// the same in two steps: raw rows with cp.async (no registers, no dependence on f's constants), then f in place
+template <int C, int ROWS, int W>
+PCD_HD void stage_rows_full(float* dst, const float* PCD_RESTRICT src, long long cs, int gy0, int H) {
+    constexpr int W4 = W / 4, P = W + 8;
+    static_assert((W4 & (W4 - 1)) == 0, "row width must be a power-of-two number of float4");
+    for_tasks<C * ROWS * W4>([&](int i) {
+        const int x4 = i % W4, row = i / W4, ch = row / ROWS, r = row - ch * ROWS;
+        const int gy = gy0 + r;
+        const bool ok = gy >= 0 && gy < H;
+        cp16(dst + row * P + 4 + 4 * x4, ok ? src + ch * cs + (long long)gy * W + 4 * x4 : src, ok);
+    });
+    for_tasks<C * ROWS * 2>([&](int i) {
+        const int row = i >> 1;
+        st4(dst + row * P + ((i & 1) ? 4 + W : 0), 0.f, 0.f, 0.f, 0.f);
+    });
+}
+template <int C, int ROWS, int W, class F>
+PCD_HD void apply_rows_full(float* dst, int gy0, int H, F f) {
+    constexpr int W4 = W / 4, P = W + 8;
+    for_tasks<C * ROWS * W4>([&](int i) {
+        const int x4 = i % W4, row = i / W4, ch = row / ROWS, r = row - ch * ROWS;
+        const int gy = gy0 + r;
+        if (gy >= 0 && gy < H) {
+            F4 v = ld4(dst + row * P + 4 + 4 * x4);
+            st4(dst + row * P + 4 + 4 * x4, f(ch, v.x), f(ch, v.y), f(ch, v.z), f(ch, v.w));
+        }
+    });
+}
+
 // ======================================================================================================
 // forward
 // ======================================================================================================
@@ -460,19 +489,24 @@ PCD_HD void fwdB_body(const PassArgs& a, int bx, int n, int z, float* smem) {
     const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
     const double cnt = (double)a.B * a.Ho * a.Wo;
     const int S = a.S, uA = half ? 2 : 0, uB = uA + 1;
+    const float* src = e.saved + slot_z(uA) * nslot + (long long)n * C * a.Ho * a.Wo;
+    constexpr int FTH_ = FTH ? FTH : 4, FW = FTW ? FTW : 4;
+    if (FAST) {      // the raw zA rows start their way into shared memory before the BN constants are derived
+        if (half == 0) stage_rows_full<C, FTH_ + 2, FW>(Q, src, (long long)a.Ho * a.Wo, g.oy0 - 1, a.Ho);
+        else stage_rows_full<C, FTH_ + 4, FW>(Q, src, (long long)a.Ho * a.Wo, g.oy0 - 2, a.Ho);
+    }
     PCD_FOR(j, C) {
         BnC b = bn_consts(e.stats, C, bn_unit(S, uA), j, cnt, a.eps);
         BNC[2 * j] = b.mean;
         BNC[2 * j + 1] = b.rstd;
     }
+    if (FAST) cp16_wait();
     PCD_SYNC();
     {
-        const float* src = e.saved + slot_z(uA) * nslot + (long long)n * C * a.Ho * a.Wo;
         auto bnrelu = [&](int ch, float v) { return relu((v - BNC[2 * ch]) * BNC[2 * ch + 1]); };
         if (FAST) {
-            constexpr int FTH_ = FTH ? FTH : 4, FW = FTW ? FTW : 4;
-            if (half == 0) load_rows_full<C, FTH_ + 2, FW>(Q, src, (long long)a.Ho * a.Wo, g.oy0 - 1, a.Ho, bnrelu);
-            else load_rows_full<C, FTH_ + 4, FW>(Q, src, (long long)a.Ho * a.Wo, g.oy0 - 2, a.Ho, bnrelu);
+            if (half == 0) apply_rows_full<C, FTH_ + 2, FW>(Q, g.oy0 - 1, a.Ho, bnrelu);
+            else apply_rows_full<C, FTH_ + 4, FW>(Q, g.oy0 - 2, a.Ho, bnrelu);
         } else {
             load_tile<FAST>(Q, src, (long long)a.Ho * a.Wo, C, IH, IW, g.oy0 - HY, g.ox0 - 4, a.Ho, a.Wo, bnrelu);
         }

@@ -288,21 +288,21 @@ PCD_HD void bwdA2_pool_job(const EdgeBwdArgs& a, const EdgeG& e, const Geo& g, i
     const double cnt = (double)a.B * a.Ho * a.Wo;
     const float beta = e.beta ? e.beta[0] : 1.f;
     const int bn = which ? bn_p2() : bn_p1();
-    PCD_FOR(j, C) {
-        edge_coef(COEF, j, dz_consts(e.stats, C, bn, j, cnt, a.eps, e.bstats[bs_s0() * C + j], e.bstats[bs_sz(bn) * C + j],
-                                     beta * e.alpha[which ? 2 : 1]));
-    }
-    if (!which) {
+    if (!which) {      // raw input tile (argmax recomputation): cp.async, in flight while the BN constants are derived
         const float* xi = e.x + (long long)g.n * e.x_ns;
         const long long xcs = (long long)a.Hs * a.Ws;
         for_tasks<C * IH * (XW / 4)>([&](int i) {
             const int c4 = i % (XW / 4), r = (i / (XW / 4)) % IH, ch = i / ((XW / 4) * IH);
             const int gy = S * g.oy0 - 4 + r, gx = 4 * c4 - 4;
-            F4 v = {0.f, 0.f, 0.f, 0.f};
-            if (gy >= 0 && gy < a.Hs && gx >= 0 && gx < a.Ws) v = ld4(xi + ch * xcs + (long long)gy * a.Ws + gx);
-            *reinterpret_cast<F4*>(XIN + (size_t)i * 4) = v;
+            const bool ok = gy >= 0 && gy < a.Hs && gx >= 0 && gx < a.Ws;
+            cp16(XIN + (size_t)i * 4, ok ? xi + ch * xcs + (long long)gy * a.Ws + gx : xi, ok);
         });
     }
+    PCD_FOR(j, C) {
+        edge_coef(COEF, j, dz_consts(e.stats, C, bn, j, cnt, a.eps, e.bstats[bs_s0() * C + j], e.bstats[bs_sz(bn) * C + j],
+                                     beta * e.alpha[which ? 2 : 1]));
+    }
+    if (!which) cp16_wait();
     PCD_SYNC();
     const float* dn_img = e.dn + (long long)g.n * e.dn_ns;
     const float* Z = e.saved + (which ? slot_p2() : slot_p1()) * nslot + (long long)g.n * C * HW;
