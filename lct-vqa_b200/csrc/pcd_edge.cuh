@@ -274,16 +274,20 @@ PCD_HD void unit_forward(const float* tile, int rows, int pitch, int halo_y, con
             P[(2 * i + 1) * (NCG * NSTRIP) + task] = q;
         }
     }
-    reduce_columns(P, P2, 8, NCG, NSTRIP, NCG * NSTRIP, [&](int grp, int k, float v) {
+    reduce_columns<(C == 16 ? 16 : 32)>(P, P2, 8, NCG, NSTRIP, NCG * NSTRIP, [&](int grp, int k, float v) {
         pcd_atomic_add(st + (k & 1) * C + grp * 4 + (k >> 1), (double)v);
     });
 }
 
 constexpr int kFwdAJobs = 5;
 
+// partial sums per column in the block reductions of the forward kernels: 16 for C = 16 keeps the 16x16 stride-1 job at
+// 75 KB (3 blocks/SM)
+PCD_HOSTDEV int fwd_np(int C) { return C == 16 ? 16 : 32; }
+
 PCD_HOSTDEV size_t fwdA_smem_floats(int C, int S, int TH, int TW) {
     const int IH = S * TH + 8, IW = S * TW + 8;
-    return (size_t)C * IH * IW + (size_t)C * TH * TW * 2 + 4 * C * 32 + C * C + 64;
+    return (size_t)C * IH * IW + (size_t)C * TH * TW * 2 + 4 * C * fwd_np(C) + C * C + 64;
 }
 
 template <int C, int S, int FTH, int FTW>
@@ -302,7 +306,7 @@ PCD_HD void fwdA_body(const PassArgs& a, int bx, int n, int z, float* smem) {
     float* T = XIN + C * IH * IW;
     float* P = T + C * NPIX;
     float* P2 = P + C * NPIX;
-    float* WS = P2 + 4 * C * 32;
+    float* WS = P2 + 4 * C * fwd_np(C);
     const long long nslot = (long long)a.B * C * a.Ho * a.Wo;
     if (FAST) {      // full-width tile; the conv jobs get relu(x) (applied once here), the pool job the raw tile
         constexpr int FIH = S * (FTH ? FTH : 4) + 8, FW = S * (FTW ? FTW : 4);
@@ -428,7 +432,7 @@ PCD_HD void fwdA_body(const PassArgs& a, int bx, int n, int z, float* smem) {
         const int NT = C * NSTRIP;
         P[0 * NT + task] = s1; P[1 * NT + task] = q1; P[2 * NT + task] = s2; P[3 * NT + task] = q2;
     }
-    reduce_columns(P, P2, 4, C, NSTRIP, C * NSTRIP, [&](int ch, int k, float v) {
+    reduce_columns<(C == 16 ? 16 : 32)>(P, P2, 4, C, NSTRIP, C * NSTRIP, [&](int ch, int k, float v) {
         const int bn = (k < 2) ? bn_p1() : bn_p2();
         pcd_atomic_add(e.stats + (bn * 2 + (k & 1)) * C + ch, (double)v);
     });
