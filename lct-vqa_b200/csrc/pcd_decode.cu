@@ -6,11 +6,13 @@
 //             shared memory for all steps, the cell state in a register)
 //             x = emb[word] (tanh only for <start>, vqa_model.py:119 vs :133);  gates = x W_ih^T + h W_hh^T + b;  h_t -> L2
 //   -- grid barrier --
-//   phase B  (every block: one 64 x 128 tile of the vocabulary)  logits = tanh(h_t) W_out^T + b_out with tanh(h_t) resident
-//             in shared memory and W_out (L2-resident: 36.6 MB at V = 17858) streamed through a cp.async double buffer;
-//             4 x 8 register tiles; row-wise argmax of the tile -> one (value, index) candidate per row and tile
+//   phase B  (every block: one 64 x 128 tile of the vocabulary)  logits = tanh(h_t) W_out^T + b_out: K chunks of 32 of
+//             (tanh(h_t) rows | W_out tile rows; W_out is L2-resident, 36.6 MB at V = 17858) stream through a 4-stage
+//             cp.async ring; 4 x 8 register tiles; row-wise argmax of the tile -> one packed (value, index) candidate per
+//             row and tile
 //   -- grid barrier --
-//   the next phase A starts by reducing the candidates (lowest index wins ties, like torch.argmax) to the new words.
+//   the next phase A starts by reducing the candidates (lowest index wins ties, like torch.argmax) to the new words;
+//   the input projection is split four ways along the embedding row (all ~19 float4 loads of a thread independent).
 // The logits are never written anywhere.  Sampling (deterministic=False, torch.multinomial) is not covered: the Python side
 // keeps that on stock torch ops.
 #include "../../include/pcdarts_sm100.h"

@@ -493,3 +493,33 @@ def decode_case(device, B, H, E, V, T, seed=3):
             cur = embd(tokens[:, t:t + 1]).transpose(0, 1)                   # teacher-force the kernel's word
     assert exact >= 0.98 * B * T, (exact, B * T)
     return exact / (B * T)
+
+
+def generate_golden_case(device, tie=1e-5):
+    """QstEncoder.generate (native greedy decode) vs the words the unmodified reference generated
+    (tests/golden/make_golden_generate.py).  A row is compared up to (excluding) the first step whose reference top-2 logit
+    margin is below `tie`; the stored margins are all above 3e-5, so at the default every word is compared."""
+    import config
+    config.DEVICE = device
+    from vqa_model import QstEncoder
+    g = load_golden("generate")
+    compared = 0
+    for n in ("a", "b"):
+        V, E, H, B, T = (int(x) for x in g[f"{n}.dims"])
+        enc = QstEncoder(V, E, H, 1, H, max_length=T)
+        sd = {k[len(n) + 1:]: torch.as_tensor(v) for k, v in g.items()
+              if k.startswith(n + ".") and k[len(n) + 1:] in enc.state_dict()}
+        assert set(sd) == set(enc.state_dict())
+        enc.load_state_dict(sd)
+        enc = enc.to(device)
+        words = enc.generate(torch.as_tensor(g[f"{n}.img"]).to(device)).cpu()
+        ref, margin = torch.as_tensor(g[f"{n}.words"]), torch.as_tensor(g[f"{n}.margin"])
+        assert words.shape == ref.shape and words.dtype == torch.long
+        for b in range(B):
+            for t in range(T):
+                if float(margin[b, t]) < tie:
+                    break
+                assert int(words[b, t]) == int(ref[b, t]), (n, b, t, int(words[b, t]), int(ref[b, t]), float(margin[b, t]))
+                compared += 1
+    assert compared >= 200
+    return compared

@@ -86,3 +86,8 @@ def test_product_refuses_cpu_without_emulation():
 def test_greedy_decode(B, H, E, V, T):
     """Host side of pcd_decode_greedy (argument marshalling, token layout, <start>/tanh convention) on the emulation build."""
     P.decode_case("cpu", B, H, E, V, T)
+
+
+def test_generate_golden():
+    """QstEncoder.generate through the decode entry point == the words of the unmodified reference's generate()."""
+    assert P.generate_golden_case("cpu") == 5 * 30 + 9 * 12

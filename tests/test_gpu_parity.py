@@ -285,3 +285,9 @@ def test_native_library_is_the_one_running():
     assert lib.pcd_is_cuda_build() == 1
     maps = open("/proc/self/maps").read()
     assert "libpcdarts_sm100.so" in maps
+
+
+def test_generate_golden():
+    """The persistent decode kernel reproduces the words the unmodified reference generated (tests/golden/generate.npz);
+    steps whose reference top-2 margin is within 1e-4 of a tie (and what follows them in that row) are not compared."""
+    P.generate_golden_case(DEV, tie=1e-4)
