@@ -91,3 +91,33 @@ def test_greedy_decode(B, H, E, V, T):
 def test_generate_golden():
     """QstEncoder.generate through the decode entry point == the words of the unmodified reference's generate()."""
     assert P.generate_golden_case("cpu") == 5 * 30 + 9 * 12
+
+
+def test_generate_falls_back_to_the_module_loop_outside_the_kernel_envelope():
+    """Hidden sizes the decode kernel does not take (not a multiple of 32) and sampled (non-deterministic) decoding run the
+    reference's own loop of stock modules; both produce (B, max_length) int64 words in range."""
+    from pcd_ops import decode_supported
+    from vqa_model import QstEncoder
+    torch.manual_seed(3)
+    q = QstEncoder(90, 8, 48, 1, 48, max_length=6)           # H = 48
+    img = 0.3 * torch.randn(4, 48)
+    assert not decode_supported(img, q.lstm, q.word2vec, q.fc1)
+    words = q.generate(img)
+    assert words.shape == (4, 6) and words.dtype == torch.long and int(words.max()) < 90
+    q2 = QstEncoder(90, 8, 32, 1, 32, deterministic=False, max_length=5)
+    img2 = 0.3 * torch.randn(3, 32)
+    assert decode_supported(img2, q2.lstm, q2.word2vec, q2.fc1)      # the shape is fine, the sampling mode is not
+    words2 = q2.generate(img2)
+    assert words2.shape == (3, 5) and int(words2.min()) >= 0 and int(words2.max()) < 90
+
+
+def test_make_capturable_moves_adam_step_counters():
+    """search.make_capturable flips an optimizer that has already stepped (host-side `step` counters) to the capturable form."""
+    from search import make_capturable
+    p = torch.nn.Parameter(torch.ones(3))
+    opt = torch.optim.Adam([p], lr=1e-3)
+    p.grad = torch.ones(3)
+    opt.step()
+    make_capturable(opt)
+    assert opt.param_groups[0]["capturable"] is True
+    assert torch.is_tensor(opt.state[p]["step"]) and opt.state[p]["step"].device == p.device
