@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-graph-dp", action="store_true", help="under data parallelism run the step eagerly instead of as a CUDA graph with the NCCL all-reduces captured inside")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the replica-checksum / averaged-gradient-vs-oracle block")
     ap.add_argument("--no-overlap", action="store_true", help="keep the weight-grad jobs on the main stream")
     return ap.parse_args()
 
@@ -74,6 +75,21 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def step_traffic(unrolled, batch):
+    """DRAM bytes per step of the MixedOp kernel group: dram__bytes_read.sum + dram__bytes_write.sum summed over the group's
+    launches in the committed whole-step ncu launch list (profiles/tools/launch_traffic.py writes the JSON from the csv).
+    None when the list for the current kernels is absent — never a stale constant."""
+    path = os.path.join(ROOT, "profiles", "r02_step_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        key = "unrolled" if unrolled else "first_order"
+        return t[key]["mixedop_group_bytes"] * batch / t["batch"], \
+            f"ncu cold-cache DRAM counters over one whole step at B={t['batch']} ({t['source']}), scaled by B/{t['batch']}"
+    except Exception:
+        return None, "no ncu launch list for the current kernels under profiles/"
 
 
 def synth_batch(seed, B, V, img):
@@ -107,32 +123,44 @@ def cpu_search_step_factory(a, B):
 
 
 def time_cpu(a, steps, warmup, budget_s):
-    """Time the oracle port on a bounded sample: the per-GPU batch is cut to B_cpu so the run fits the budget."""
+    """Time the oracle port of the reference's CPU path on the FULL per-GPU batch, all host cores.
+
+    The sample is bounded by timing fewer steps, never fewer samples (cost is not linear in the batch on a CPU): at most
+    `steps` steps, stopping early once the next one would overrun `budget_s`; at least one.  The same function serves the
+    `cpu_baseline` of the GPU arm (steps=1) and `--impl reference`, so the two numbers of one record agree.  Only when a
+    single full-batch step cannot fit the budget at all is the batch halved (and the scaling stated)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     t0 = time.time()
-    probe = cpu_search_step_factory(a, 1)
-    t1 = time.time()
-    probe()                                  # first call: allocator / thread-pool / dispatch warm-up
+    probe = cpu_search_step_factory(a, min(2, a.batch))
+    probe()                                  # allocator / thread-pool / dispatch warm-up (2 samples, untimed)
     t1 = time.time()
     probe()
-    per_sample = time.time() - t1            # one sample, warm
-    B = 1
-    for cand in (2, 4, 8, 16, 32, 64):
-        if cand <= a.batch and per_sample * cand * 0.6 * (steps + warmup) <= budget_s:
-            B = cand
-    step = cpu_search_step_factory(a, B) if B > 1 else probe
-    for _ in range(warmup):
+    per_sample = (time.time() - t1) / min(2, a.batch)
+    B = a.batch
+    while B > 2 and per_sample * B * 0.5 > budget_s:       # 0.5: measured, large batches amortise per-op overheads
+        B //= 2
+    step = cpu_search_step_factory(a, B)
+    t_begin = time.time()
+    done_w = 0
+    if warmup > 0 and per_sample * B * 0.5 * 3 <= budget_s:   # one full-size warm-up step when three steps fit
         step()
-    t = time.time()
-    for _ in range(steps):
+        done_w = 1
+    times = []
+    for _ in range(max(1, steps)):
+        if times and (time.time() - t_begin) + sum(times) / len(times) > budget_s:
+            break
+        t = time.time()
         step()
-    dt = (time.time() - t) / steps
+        times.append(time.time() - t)
+    dt = sum(times) / len(times)
     value = (1.0 / dt) * (B / a.batch)
-    return value, dt, {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                       "sample": f"{steps} step(s) (+{warmup} warm-up) of the same search step on {B} of the "
-                                 f"{a.batch} samples of the batch, {dt:.2f} s each; value = steps/s scaled by "
-                                 f"{B}/{a.batch} (cost is linear in the batch); setup and probe {t - t0 - 0.0:.1f} s not timed"}
+    note = "" if B == a.batch else f"; ONE full-batch step exceeds the {budget_s:.0f} s budget on this host, value scaled by {B}/{a.batch}"
+    return value, dt, {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "steps_timed": len(times),
+                       "samples_per_step": B,
+                       "sample": f"{len(times)} timed step(s) (+{done_w} full-size warm-up) of the same search step on {B} of the "
+                                 f"{a.batch} samples of the batch, {dt:.2f} s each, {cores} threads{note}; model setup and a "
+                                 f"2-sample warm-up ({t_begin - t0:.1f} s) not timed"}
 
 
 def run_reference(a):
@@ -142,7 +170,7 @@ def run_reference(a):
     value, dt, cb = time_cpu(a, a.steps, a.warmup, budget_s=150.0)
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps_timed": cb["steps_timed"], "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload(a, a.gpus), "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
@@ -314,14 +342,17 @@ def run_b200(a):
         n_bwd = 5 if unrolled else 2
         alg_mb = (n_fwd * MIXED_FWD_MB_B64 + n_bwd * MIXED_BWD_MB_B64) * a.batch / 64.0
         achieved = alg_mb / 1e3 / (mixed_ms / 1e3)
-        top = next(iter(by_kernel))
+        fam = {}
+        for k, (t, c) in prof.items():       # kernel families: template / geometry suffixes (_c4, _s1, ...) folded together
+            if k.startswith(MIXED_KERNELS):
+                f = next(m for m in MIXED_KERNELS if k.startswith(m))
+                fam[f] = fam.get(f, 0.0) + t / nprof
+        top = max(fam, key=fam.get) if fam else next(iter(by_kernel))
+        traffic, traffic_note = step_traffic(unrolled, a.batch)
         roofline = {"bound": "hbm", "kernel": "MixedOp kernel group (fwdA,fwdB,combine | node_stats,bwdB,bwdA,wgrad,"
                                               "source_grad,arch_grads): all 56 edges x all passes of one step",
                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                    # DRAM bytes of the same kernel group from ncu (dram__bytes_read + dram__bytes_write, cold cache): one forward
-                    # + one full backward = 9.15 GB, of which 1.88 GB weight-grad jobs (profiles/r01_v6_ncu_launches_summary.txt)
-                    "traffic": ((3 if unrolled else 2) * 9.15e9 + (2 if unrolled else 0) * (9.15e9 - 1.88e9)) * a.batch / 64.0,
-                    "traffic_note": "bytes per step of the kernel group, ncu cold-cache DRAM counters at B=64 scaled by B/64",
+                    "traffic": traffic, "traffic_note": traffic_note, "ms_by_family": fam,
                     "algorithmic_mb_per_step": alg_mb, "kernel_ms_per_step": mixed_ms, "peak_source": peak_src,
                     "passes_per_step": {"forward": n_fwd, "backward": n_bwd},
                     "dominant_kernel": top, "native_kernel_ms_per_step": total_ms / nprof,
@@ -345,15 +376,19 @@ def run_b200(a):
             extras["lct_alpha_step"] = lct_alpha_step_bench(a, dev)
         except Exception as e:      # the headline numbers above do not depend on it
             extras["lct_alpha_step"] = {"error": repr(e)[:200]}
+    parity = None
+    if world > 1 and not a.no_parity:
+        parity = dp_parity(a, model, reducer, rank, world, dev)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        _, _, cpu = time_cpu(a, 1, 0, budget_s=20.0)
+        _, _, cpu = time_cpu(a, 1, 0, budget_s=45.0)
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": workload(a, world), "e2e": e2e, "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
                "wgrad_overlap": not a.no_overlap, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
-               "comm": None if reducer is None else {"allreduce_calls": reducer.calls, "allreduce_bytes": reducer.bytes}}
+               "parity": parity,
+               "comm": None if reducer is None else reducer.report()}
         emit(out)
     if world > 1:
         torch.cuda.synchronize()
@@ -365,6 +400,68 @@ def run_b200(a):
             sys.stderr.flush()
             os._exit(0)
         dist.destroy_process_group()
+
+
+def dp_parity(a, model, reducer, rank, world, dev, shard_batch=8):
+    """NCCL parity evidence, after the timed steps, on every rank (it contains collectives):
+      1. replica consistency: per-rank fp64 checksums (sum, sum of squares, over every weight and alpha/beta) all-gathered;
+         data-parallel replicas must stay BIT-identical;
+      2. one w-step forward/backward on a fresh shard of `shard_batch` samples per rank (dropout off), gradients averaged by
+         the GradReducer over NCCL, compared on rank 0 with the oracle's gradients of the same `world` shards averaged by hand
+         (the only place this arm executes oracle/: as the checker)."""
+    import torch.distributed as dist
+    with torch.no_grad():
+        tensors = [p.detach() for p in model.parameters()] + [t.detach() for t in model.arch_parameters()]
+        cs = torch.stack([torch.stack([t.double().sum() for t in tensors]).sum(),
+                          torch.stack([(t.double() ** 2).sum() for t in tensors]).sum()])
+    gathered = [torch.zeros_like(cs) for _ in range(world)]
+    dist.all_gather(gathered, cs)
+    out = {"replica_checksums": [[float(x) for x in g.tolist()] for g in gathered],
+           "replicas_identical": all(torch.equal(g, gathered[0]) for g in gathered)}
+    params = list(model.parameters())
+    p_drop, model.dropout.p = model.dropout.p, 0.0
+    try:
+        for p_ in params:
+            p_.grad = None
+        batch = [t.to(dev) for t in synth_batch(5000 + rank, shard_batch, a.vocab, a.img)]
+        loss = model._loss(*batch)
+        loss.backward()
+        grads = [p_.grad if p_.grad is not None else torch.zeros_like(p_) for p_ in params]
+        reducer(grads)
+        torch.cuda.synchronize()
+    finally:
+        model.dropout.p = p_drop
+    if rank == 0:
+        from oracle import pcdarts_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        par, buf = O.split_state(sd)
+        keys = [k for k, _ in model.named_parameters()]
+        for v in par.values():
+            v.requires_grad_(True)
+        arch = [t.detach().cpu().clone() for t in model.arch_parameters()]
+        acc = None
+        for r in range(world):
+            b = synth_batch(5000 + r, shard_batch, a.vocab, a.img)
+            bns = O.BNState({k: v.clone() for k, v in buf.items()})
+            l_r = O.vqa_loss(par, bns, arch, *b, dropout_p=0.0)
+            g_r = torch.autograd.grad(l_r, [par[k] for k in keys], allow_unused=True)
+            g_r = [torch.zeros_like(par[k]) if g is None else g for g, k in zip(g_r, keys)]
+            acc = g_r if acc is None else [x + y for x, y in zip(acc, g_r)]
+            if r == 0:
+                out["rank0_loss_rel_err"] = abs(float(loss) - float(l_r)) / abs(float(l_r))
+        errs = []
+        for k, g, ref in zip(keys, grads, acc):
+            ref = ref / world
+            den = float(ref.abs().max())
+            errs.append((float((g.cpu() - ref).abs().max()) / den if den > 0 else float(g.abs().max()), k))
+        errs.sort(reverse=True)
+        out["averaged_grads_vs_oracle"] = {
+            "tensors": len(errs), "share_within_1e-4": sum(e <= 1e-4 for e, _ in errs) / len(errs), "worst": errs[:3],
+            "shards": world, "samples_per_shard": shard_batch,
+            "note": "search-net tensors beyond 1e-4 are ReLU / max-pool tie flips (~1/sqrt(B*H*W), DESIGN.md §2)"}
+    dist.barrier()
+    return out
 
 
 def lct_alpha_step_bench(a, dev, iters=3):

@@ -131,10 +131,15 @@ class VqaModel(nn.Module):
     def arch_parameters(self):
         return self.img_encoder.darts.arch_parameters()
 
-    def _loss(self, images, questions, labels):
+    def _loss(self, images, questions, labels, qst_only=False):
+        """models_lct.py:253-260.  `qst_only` is not part of the reference signature: the darts_vqa-flavour Architect that
+        get_architect returns under SKIP_STAGE2 passes it (always False there); True keeps only the next-word loss."""
         img_feature = self.img_encoder(images)
         qst_feature, states = self.qst_encoder(questions, img_feature, return_states=True)
-        return self.criterion(self._answer(img_feature, qst_feature), labels) + self.qst_encoder.next_word_loss(states, questions)
+        qst_loss = self.qst_encoder.next_word_loss(states, questions)
+        if qst_only:
+            return qst_loss
+        return self.criterion(self._answer(img_feature, qst_feature), labels) + qst_loss
 
     def new(self):
         twin = VqaModel(self.embed_size, self.qst_vocab_size, self.ans_vocab_size, self.word_embed_size, self.num_layers,

@@ -61,3 +61,6 @@ class GradReducer:
                                           zip(flat.split_with_sizes([t.numel() for t in bucket]), bucket)])
         self.calls += 1
         self.bytes += flat.numel() * 4
+
+    def report(self):
+        return {"allreduce_calls": self.calls, "allreduce_bytes": self.bytes}

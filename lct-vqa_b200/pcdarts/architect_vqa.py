@@ -102,13 +102,15 @@ class Architect(object):
                                          eta, network_optimizer)
         else:
             self._backward_step(img_valid, qst_valid, label_valid)
+        pcd_ops.overlap_join(img_valid)        # no deferred weight-grad job of this step outlives it
         self.optimizer.step()
 
     def _backward_step(self, img_valid, qst_valid, label_valid):
         # first-order: d L_val / d alpha at the current weights (architect_vqa.py:53-55)
         arch = self.model.arch_parameters()
-        loss = self.model._loss(img_valid, qst_valid, label_valid)
-        grads = torch.autograd.grad(loss, arch)
+        with pcd_ops.weight_grads(False):      # only d/d(alpha, beta): activation-only cell backward, no weight-grad jobs
+            loss = self.model._loss(img_valid, qst_valid, label_valid)
+            grads = torch.autograd.grad(loss, arch)
         self._allreduce(list(grads))
         for a, g in zip(arch, grads):
             a.grad = g

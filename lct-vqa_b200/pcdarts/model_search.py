@@ -187,7 +187,10 @@ class Network(_ArenaModule):
         (self.alphas_normal, self.alphas_reduce, self.betas_normal, self.betas_reduce) = self._arch_parameters
 
     def new(self):
-        twin = Network(self._C, self._num_classes, self._layers).to(config.DEVICE)
+        # basic_vqa passes the owning VqaModel on to the twin (basic_vqa model_search.py:139-141); darts_vqa has none
+        owner = self._vqa_model() if hasattr(self, '_vqa_model') else None
+        extra = (owner,) if owner is not None else ()
+        twin = Network(self._C, self._num_classes, self._layers, *extra).to(config.DEVICE)
         for mine, theirs in zip(twin.arch_parameters(), self.arch_parameters()):
             mine.data.copy_(theirs.data)
         return twin

@@ -39,13 +39,42 @@ class SearchStep:
         return self.w_step(*train_batch)
 
 
+class _TrainingState:
+    """Snapshot of everything a training step mutates (weights, BN buffers, alphas/betas, optimizer moments and step
+    counters), restorable IN PLACE — the tensors keep their addresses, so a CUDA graph captured afterwards still points
+    at them.  Used to undo the warm-up steps a graph capture needs: construction must not consume training steps."""
+
+    def __init__(self, modules, arch_tensors, optimizers):
+        self.tensors = []
+        for m in modules:
+            self.tensors += [p.data for p in m.parameters()] + list(m.buffers())
+        self.tensors += [a.data for a in arch_tensors]
+        self.saved = [t.clone() for t in self.tensors]
+        self.optimizers = list(optimizers)
+        self.opt_saved = [{id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                           for p, st in opt.state.items()} for opt in self.optimizers]
+
+    def restore(self):
+        with torch.no_grad():
+            torch._foreach_copy_(self.tensors, self.saved)
+            for opt, saved in zip(self.optimizers, self.opt_saved):
+                for p, st in opt.state.items():
+                    old = saved.get(id(p), {})
+                    for k, v in st.items():
+                        if torch.is_tensor(v):      # state created by the warm-up goes back to its initial zeros
+                            v.copy_(old[k]) if k in old else v.zero_()
+
+
 class GraphedSearchStep:
     """The whole search step (alpha-step + w-step, ~4000 kernel launches and a few thousand torch ops) captured
     once in a CUDA graph and replayed: the step is otherwise host-bound.  Inputs are copied into static device
     buffers; the learning rate is baked in at capture (re-capture when the schedule changes it).
 
-    Requirements: optimizers created with capturable=True (Adam keeps its step counter on the device), a
-    single process (no collectives inside the capture), shapes fixed.
+    Requirements: optimizers created with capturable=True (Adam keeps its step counter on the device), shapes
+    fixed.  Under data parallelism the NCCL all-reduces of the GradReducer are captured with the rest (bench.py does
+    so at N > 1).  The warm-up steps the capture needs run on the first batch and are then UNDONE: weights, BN buffers,
+    alphas and both optimizers' state are restored in place, so the first replay is training step 1 exactly as in the
+    eager path (dropout draws aside).
     """
 
     def __init__(self, step, train_batch, valid_batch, lr, unrolled=True, warmup=3):
@@ -57,9 +86,12 @@ class GraphedSearchStep:
         # high priority: with weight-grad overlap on, the library's low-priority stream only fills the SMs this one leaves idle
         side = torch.cuda.Stream(priority=-1)
         side.wait_stream(torch.cuda.current_stream())
+        modules = [step.model] + ([step.architect._twin] if getattr(step.architect, "_twin", None) is not None else [])
+        snap = _TrainingState(modules, step.model.arch_parameters(), [step.optimizer, step.architect.optimizer])
         with torch.cuda.stream(side):                 # warm-up on a side stream (allocator, cuDNN/cuBLAS handles)
             for _ in range(warmup):
                 step.step(self.train, self.valid, lr, unrolled)
+            snap.restore()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -100,9 +132,12 @@ class GraphedLctStep:
         make_capturable(architect.optimizer)
         side = torch.cuda.Stream(priority=-1)
         side.wait_stream(torch.cuda.current_stream())
+        snap = _TrainingState([architect.ef_model, architect.w_model], architect.ef_model.arch_parameters(),
+                              [architect.optimizer])      # ArchitectLct.step only steps the architecture optimizer
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 architect.step(*self.train, *self.valid, ef_lr, w_lr)
+            snap.restore()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()

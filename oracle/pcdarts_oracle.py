@@ -333,13 +333,19 @@ def architect_step(P, bns, arch, adam_state, train, valid, eta, param_keys, unro
     return g
 
 
-def w_step(P, bns, arch, batch, adam_state, param_keys, lr=1e-3, clip=5.0, **kw):
+def w_step(P, bns, arch, batch, adam_state, param_keys, lr=1e-3, clip=5.0, debug=None, **kw):
     """The w-step of Experiment.train, darts_vqa/experiment.py:187-200."""
     ws = [P[k] for k in param_keys]
     loss = vqa_loss(P, bns, arch, *batch, **kw)
-    gs = _grads(loss, ws)
+    if debug is not None:      # loss.backward() of the reference also accumulates into the alphas' / betas' .grad
+        got = _grads(loss, ws + list(arch))
+        gs, debug["arch_grads"] = got[:len(ws)], got[len(ws):]
+    else:
+        gs = _grads(loss, ws)
     total = torch.norm(torch.stack([g.norm(2) for g in gs]), 2)
     coef = torch.clamp(clip / (total + 1e-6), max=1.0)      # nn.utils.clip_grad_norm_
+    if debug is not None:
+        debug.update(grads=[g.clone() for g in gs], total_norm=total.clone(), clip_coef=coef.clone())
     with torch.no_grad():
         adam_step(ws, [g * coef for g in gs], adam_state, lr, betas=(0.9, 0.999))
     return loss.detach()

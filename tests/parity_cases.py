@@ -139,7 +139,7 @@ def network_vs_oracle(B, H, device, seed=17):
         pcd_ops._DEBUG_KEEP = None
     assert len(keep) == 4
     named = dict(net.named_parameters())
-    worst, errs = (0.0, ""), []
+    worst, errs, errs64, oracle64 = (0.0, ""), [], [], []
     for idx, k in enumerate(keep):                        # backward order: last cell first
         ci = 3 - idx
         _, _, _, red, rp = k["cfg"]
@@ -150,6 +150,14 @@ def network_vs_oracle(B, H, device, seed=17):
         ins = [k[n].detach().cpu().requires_grad_(True) for n in ("s0", "s1", "w", "w2")]
         yc = O.cell_forward(cpar, O.BNState(cbuf), "", *ins, bool(red), bool(rp))
         (yc * k["gout"].cpu()).sum().backward()
+        # the same cell once more in float64: the yardstick that shows what ANY fp32 evaluation can reproduce
+        dpar, dbuf = O.split_state({kk[len(pre):]: (vv.double() if vv.is_floating_point() else vv.clone())
+                                    for kk, vv in sd0.items() if kk.startswith(pre)})
+        for v in dpar.values():
+            v.requires_grad_(True)
+        dins = [k[n].detach().cpu().double().requires_grad_(True) for n in ("s0", "s1", "w", "w2")]
+        yd = O.cell_forward(dpar, O.BNState(dbuf), "", *dins, bool(red), bool(rp))
+        (yd * k["gout"].cpu().double()).sum().backward()
         npix = yc.shape[0] * yc.shape[2] * yc.shape[3]          # samples behind every weight-grad sum of this cell
         for n, p_ in cpar.items():
             e = rel_err(named[pre + n].grad, p_.grad)
@@ -157,12 +165,23 @@ def network_vs_oracle(B, H, device, seed=17):
             assert e <= 5.0 / npix ** 0.5, f"{pre}{n}: rel err {e:.3e} (beyond what a few flipped decisions explain)"
             errs.append(e)
             worst = max(worst, (e, pre + n))
+            errs64.append(rel_err(named[pre + n].grad, dpar[n].grad))
+            oracle64.append(rel_err(p_.grad, dpar[n].grad))
         for a_, b_ in (("gs0", ins[0]), ("gs1", ins[1])):      # a flipped decision perturbs a small neighbourhood: sparse
             d = (k[a_].detach().cpu().double() - b_.grad.double()).abs()
             bad = (d > REL_TOL * b_.grad.abs().max().double()).double().mean().item()
             assert bad <= 1e-3, f"{pre}{a_}: {bad:.2%} of the elements differ by more than rel {REL_TOL}"
     within = sum(e <= REL_TOL for e in errs) / len(errs)
     assert within >= 0.95, f"only {within:.1%} of the weight grads are within rel {REL_TOL}"
+    # evidence for the relaxed criterion: against the float64 evaluation the fp32 ORACLE misses rel
+    # 1e-4 on a handful of tensors too, by the same ~1/sqrt(npix) amounts; this implementation is not worse in kind
+    out_ours = sum(e > REL_TOL for e in errs64)
+    out_oracle = sum(e > REL_TOL for e in oracle64)
+    assert out_ours <= 2 * out_oracle + 4, (out_ours, out_oracle)
+    assert max(errs64) <= max(3.0 * max(oracle64), 10 * REL_TOL), (max(errs64), max(oracle64))
+    network_vs_oracle.evidence = dict(tensors=len(errs), ours_vs_fp64_outliers=out_ours, oracle32_vs_fp64_outliers=out_oracle,
+                                      ours_vs_fp64_max=max(errs64), oracle32_vs_fp64_max=max(oracle64),
+                                      ours_vs_oracle32_outliers=sum(e > REL_TOL for e in errs))
     return worst, within
 
 
@@ -523,3 +542,136 @@ def generate_golden_case(device, tie=1e-5):
                 compared += 1
     assert compared >= 200
     return compared
+
+
+# ---- one whole search step at the BENCHMARKED configuration vs the oracle -------------------------------------------
+# (VqaModel / Architect / w-step were only pinned at toy sizes, where every Linear is below the
+# tensor-core threshold; this runs exactly what bench.py times — B = 64, 64x64, V = 17858, hidden 512 — eagerly and as
+# a CUDA-graph replay, against oracle.architect_step + oracle.w_step on the same tensors.)
+FULL_DIMS = dict(embed_size=512, ans_vocab_size=1000, word_embed_size=300, num_layers=1, hidden_size=512)
+_FULL_CACHE = {}
+
+
+def full_batch(seed, B, V, img):
+    g = _gen(seed)
+    image = torch.randn(B, 3, img, img, generator=g)
+    qst = torch.randint(0, V, (B, 30), generator=g)
+    qst[:, 0] = 2
+    lbl = torch.randint(0, FULL_DIMS["ans_vocab_size"] if V > 100 else 12, (B,), generator=g)
+    return image, qst, lbl
+
+
+def _oracle_search_step(unrolled, B, V, img, dims):
+    """oracle: alpha-step then w-step from a seeded state; cached (the eager and the graph test share it)."""
+    key = (unrolled, B, V, img, tuple(sorted(dims.items())))
+    if key in _FULL_CACHE:
+        return _FULL_CACHE[key]
+    sd = O.alloc_state(O.vqa_spec(qst_vocab_size=V, **dims), seed=700)
+    par, buf = O.split_state(sd)
+    init = {k: v.clone() for k, v in sd.items()}
+    for v in par.values():
+        v.requires_grad_(True)
+    gen = _gen(701)
+    arch = [(1e-1 * torch.randn(s, generator=gen)).requires_grad_(True) for s in ((14, 8), (14, 8), (14,), (14,))]
+    arch0 = [a.detach().clone() for a in arch]
+    train, valid = full_batch(702, B, V, img), full_batch(703, B, V, img)
+    keys = list(par.keys())
+    bns = O.BNState(buf)
+    dbg_a, dbg_w = {}, {}
+    kw = dict(dropout_p=0.0)
+    if unrolled:
+        kw["debug"] = dbg_a
+    g = O.architect_step(par, bns, arch, {}, train, valid, 1e-3, keys, unrolled=unrolled, **kw)
+    arch_after = [a.detach().clone() for a in arch]
+    loss = O.w_step(par, bns, arch, train, {}, keys, debug=dbg_w, dropout_p=0.0)
+    res = dict(init=init, arch0=arch0, train=train, valid=valid, keys=keys, darch=[t.detach() for t in g],
+               arch_after=arch_after, loss=loss, wgrads=[t * dbg_w["clip_coef"] for t in dbg_w["grads"]],
+               total_norm=dbg_w["total_norm"], warch=dbg_w["arch_grads"], buf_after={k: v.clone() for k, v in bns.state.items()}, dbg=dbg_a)
+    _FULL_CACHE[key] = res
+    return res
+
+
+def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims=None):
+    from argparse import Namespace
+    import config
+    config.DEVICE = device
+    from pcdarts.architect_vqa import Architect
+    from search import GraphedSearchStep, SearchStep
+    from vqa_model import VqaModel
+    dims = dict(FULL_DIMS if dims is None else dims)
+    dims.pop("qst_vocab_size", None)
+    ref = _oracle_search_step(unrolled, B, V, img, dims)
+    m = VqaModel(qst_vocab_size=V, img_encoder_type="darts", **dims).train()
+    assert list(dict(m.named_parameters()).keys()) == ref["keys"], "parameter registration order differs from the reference"
+    m.load_state_dict(ref["init"])
+    m.to(device)
+    m.dropout.p = 0.0
+    for a, v in zip(m.arch_parameters(), ref["arch0"]):
+        a.data.copy_(v)
+    arch = Architect(m, Namespace(arch_learn_rate=6e-4, arch_wt_decay=1e-3, qst_only=False))
+    if graphed:
+        arch.optimizer = torch.optim.Adam(m.arch_parameters(), lr=6e-4, betas=(0.5, 0.999), weight_decay=1e-3, capturable=True)
+    if unrolled:
+        arch.unrolled_model().dropout.p = 0.0
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=graphed)
+    step = SearchStep(m, arch, opt)
+    train = [t.to(device) for t in ref["train"]]
+    valid = [t.to(device) for t in ref["valid"]]
+    if graphed:
+        runner = GraphedSearchStep(step, train, valid, 1e-3, unrolled=unrolled, warmup=2)     # warm-up is undone
+        loss = runner()
+        torch.cuda.synchronize()
+    else:
+        step.alpha_step(train, valid, 1e-3, unrolled=unrolled)
+        for i, a in enumerate(m.arch_parameters()):           # the alpha-step's own gradient, before the w-step adds to .grad
+            assert_close(a.grad, ref["darch"][i], REL_TOL, f"alpha-step darch{i}")
+        loss = step.w_step(*train)
+    report = {}
+    # ---- alpha-step ----
+    if unrolled:
+        d, L = ref["dbg"], arch.last
+        assert_close(L["unrolled_loss"], d["loss2"], 1e-5, "L_val(w')")
+        R_ref = float(d["R"])
+        assert_close(L["vnorm"], torch.tensor(1e-2 / R_ref), REL_TOL, "|dL_val/dw'|")
+        R = float(L["R"])
+        gmax = 0.0
+        for i in range(4):
+            assert_close(L["g_pos"][i], d["g_pos"][i], REL_TOL, f"g+[{i}]")
+            assert_close(L["g_neg"][i], d["g_neg"][i], REL_TOL, f"g-[{i}]")
+            gmax = max(gmax, float(d["g_pos"][i].abs().max()) + float(d["g_neg"][i].abs().max()))
+        for i in range(4):       # raw finite difference: cancellation-aware bound (SURVEY.md App. C)
+            hv = (L["g_pos"][i] - L["g_neg"][i]).cpu() / (2 * R)
+            hr = (d["g_pos"][i] - d["g_neg"][i]) / (2 * R_ref)
+            assert (hv - hr).abs().max().item() <= REL_TOL * gmax / (2 * R_ref), f"hvp[{i}]"
+    for i, a in enumerate(m.arch_parameters()):
+        # .grad holds the alpha-step's gradient PLUS what the w-step's loss.backward() accumulated on top of it
+        # (experiment.py:195 does the same in the reference; the next alpha-step zeroes it)
+        assert_close(a.grad, ref["darch"][i] + ref["warch"][i], REL_TOL, f"darch{i}")
+        assert_close(a.detach(), ref["arch_after"][i], 1e-5, f"arch_after{i}")
+    # ---- w-step ----
+    assert_close(loss, ref["loss"], 1e-5, "w-step loss")
+    named = dict(m.named_parameters())
+    errs, worst = [], (0.0, "")
+    floor = 5.0 / (B * (img // 4) ** 2) ** 0.5        # one flipped ReLU / max-pool tie in the smallest cell (DESIGN.md §2)
+    for k, gr in zip(ref["keys"], ref["wgrads"]):
+        gp = named[k].grad
+        if gp is None:
+            assert float(gr.abs().max()) == 0.0, k
+            continue
+        e = rel_err(gp, gr) if float(gr.abs().max()) > 0 else float(gp.abs().max())
+        if ".darts." in k:
+            assert e <= max(floor, REL_TOL), f"{k}: rel err {e:.3e}"
+            errs.append(e)
+        else:
+            assert e <= REL_TOL, f"{k}: rel err {e:.3e}"
+        worst = max(worst, (e, k))
+    within = sum(e <= REL_TOL for e in errs) / max(1, len(errs))
+    assert within >= 0.95, f"only {within:.1%} of the search-network weight grads are within rel {REL_TOL}"
+    sd = m.state_dict()
+    nbt = "img_encoder.darts.stem.1.num_batches_tracked"
+    assert int(sd[nbt]) == int(ref["buf_after"][nbt]) == (4 if unrolled else 2)
+    for k in ("img_encoder.darts.stem.1.running_mean", "img_encoder.darts.stem.1.running_var",
+              "img_encoder.darts.cells.3._ops.13._ops.5.op.7.running_var", "img_encoder.darts.cells.1.preprocess1.op.2.running_mean"):
+        assert_close(sd[k], ref["buf_after"][k], 1e-5, k)
+    report.update(worst_wgrad=worst, wgrads_within=within)
+    return report

@@ -121,3 +121,57 @@ def test_make_capturable_moves_adam_step_counters():
     make_capturable(opt)
     assert opt.param_groups[0]["capturable"] is True
     assert torch.is_tensor(opt.state[p]["step"]) and opt.state[p]["step"].device == p.device
+
+
+@pytest.mark.parametrize("unrolled", [True, False])
+def test_search_step_vs_oracle_emulated(unrolled):
+    """The logic of the full-size GPU test (tests/test_gpu_parity.py::test_search_step_full_size_vs_oracle) at a size the
+    emulation finishes in seconds: one alpha-step + w-step of SearchStep against oracle.architect_step + oracle.w_step."""
+    P.search_step_vs_oracle("cpu", unrolled, graphed=False, B=2, V=40, img=32, dims=dict(P.VQA_DIMS, qst_vocab_size=None))
+
+
+def test_skip_stage2_architect_runs_an_unrolled_step():
+    """config.SKIP_STAGE2: get_architect hands the darts_vqa-flavour Architect an EF model whose _loss takes the
+    reference's three arguments (basic_vqa/pcdarts/architect.py:25,62,98); its unrolled step must run."""
+    import config
+    from architect_factory import get_architect
+    ef, w, _ = P.make_lct("cpu")
+    keep = config.SKIP_STAGE2
+    config.SKIP_STAGE2 = True
+    try:
+        arch = get_architect(ef, w, None, None)
+    finally:
+        config.SKIP_STAGE2 = keep
+    assert type(arch).__name__ == "Architect"
+    before = [a.detach().clone() for a in ef.arch_parameters()]
+    arch.unrolled_model()
+    for mod in arch.unrolled_model().modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    arch.step(*P.lct_batch(21, "cpu"), *P.lct_batch(22, "cpu"), 1e-3, None, unrolled=True)
+    assert all(a.grad is not None and torch.isfinite(a.grad).all() for a in ef.arch_parameters())
+    assert any(not torch.equal(a.detach(), b) for a, b in zip(ef.arch_parameters(), before))
+    twin = ef.img_encoder.darts.new()           # Network.new() keeps the owning-model back reference (basic_vqa model_search.py:139-141)
+    assert twin._vqa_model() is ef.img_encoder.darts._vqa_model()
+
+
+def test_graph_warmup_state_is_restored():
+    """search._TrainingState: what GraphedSearchStep uses to undo its warm-up steps (weights, buffers, alphas, Adam state)."""
+    from search import _TrainingState
+    lin = torch.nn.Linear(3, 2)
+    bn = torch.nn.BatchNorm1d(2)
+    mod = torch.nn.Sequential(lin, bn)
+    alpha = torch.zeros(4, requires_grad=True)
+    opt = torch.optim.Adam(list(mod.parameters()) + [alpha], lr=0.1)
+    snap = _TrainingState([mod], [alpha], [opt])
+    ref = [t.clone() for t in snap.tensors]
+    for _ in range(2):
+        opt.zero_grad()
+        (mod(torch.randn(5, 3)).sum() + alpha.sum()).backward()
+        opt.step()
+    assert int(bn.num_batches_tracked) == 2
+    snap.restore()
+    assert all(torch.equal(a, b) for a, b in zip(snap.tensors, ref))
+    assert int(bn.num_batches_tracked) == 0
+    for st in opt.state.values():
+        assert float(st["step"]) == 0 and float(st["exp_avg"].abs().max()) == 0 and float(st["exp_avg_sq"].abs().max()) == 0

@@ -28,6 +28,7 @@ def test_network_full_size_vs_oracle():
     through the oracle on the tensors it actually received."""
     worst, within = P.network_vs_oracle(64, 64, DEV)
     print("worst weight-grad error over the four cells:", worst, "share within 1e-4:", within)
+    print("fp64 yardstick:", P.network_vs_oracle.evidence)
 
 
 def test_shuffle_bit_exact():
@@ -291,3 +292,15 @@ def test_generate_golden():
     """The persistent decode kernel reproduces the words the unmodified reference generated (tests/golden/generate.npz);
     steps whose reference top-2 margin is within 1e-4 of a tie (and what follows them in that row) are not compared."""
     P.generate_golden_case(DEV, tie=1e-4)
+
+
+# ---- the benchmarked configuration itself (B = 64, 64x64, V = 17858, hidden 512): one whole search step vs the oracle ----
+@pytest.mark.parametrize("graphed", [False, True])
+@pytest.mark.parametrize("unrolled", [True, False])
+def test_search_step_full_size_vs_oracle(unrolled, graphed):
+    """alpha-step (unrolled with the finite-difference HVP, or first-order) + w-step exactly as bench.py runs them — eagerly
+    and replayed from the CUDA graph — against oracle.architect_step + oracle.w_step on the same tensors: L_val(w'), |v|,
+    g+, g- (rel 1e-4), the raw HVP (cancellation-aware bound), d alpha / d beta (1e-4), alphas after Adam (1e-5), the w-step
+    loss (1e-5), every clipped weight gradient (1e-4; search-network tensors with the tie-flip criterion), BN side effects."""
+    rep = P.search_step_vs_oracle(DEV, unrolled, graphed)
+    print("full-size search step:", rep)
