@@ -317,7 +317,9 @@ def arch_grad_unrolled(P, bns, arch, train, valid, eta, param_keys, r=1e-2, qst_
         for w, v in zip(ws, vector):
             w.add_(v, alpha=R)
     if debug is not None:
-        debug.update(g_pos=g_pos, g_neg=g_neg, R=R, dalpha=[d.clone() for d in dalpha], loss2=loss2)
+        debug.update(g_pos=g_pos, g_neg=g_neg, R=R, dalpha=[d.clone() for d in dalpha], loss2=loss2,
+                     w_prime={k: P2[k].detach().clone() for k in param_keys},
+                     bn_prime=None if bns2.state is None else {k: v.clone() for k, v in bns2.state.items()})
     return [d - eta * (gp - gn) / (2 * R) for d, gp, gn in zip(dalpha, g_pos, g_neg)]
 
 

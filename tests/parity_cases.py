@@ -581,12 +581,27 @@ def _oracle_search_step(unrolled, B, V, img, dims):
     kw = dict(dropout_p=0.0)
     if unrolled:
         kw["debug"] = dbg_a
+    buf_before = {k: v.clone() for k, v in buf.items()}
     g = O.architect_step(par, bns, arch, {}, train, valid, 1e-3, keys, unrolled=unrolled, **kw)
     arch_after = [a.detach().clone() for a in arch]
+    # float64 yardstick for d L_val / d(alpha, beta): the SAME oracle code evaluated in double at the point where the
+    # fp32 oracle took that gradient (w' for the unrolled step, w for the first-order one).  Measured at B = 64: the fp32
+    # oracle is 1e-4 .. 1e-3 away from it (ReLU / max-pool ties that fp32 rounding flips, summed over 10^6 pixels), while
+    # two fp32 runs with different thread counts agree to 1e-6 -- so "rel 1e-4 against the fp32 oracle" is not a property
+    # any other correct fp32 implementation can have at this size; the test bounds our error by the oracle's own.
+    w64 = dbg_a["w_prime"] if unrolled else init
+    b64 = dbg_a["bn_prime"] if unrolled else buf_before
+    P64 = {k: w64[k].double() for k in keys}
+    B64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in b64.items()}
+    a64 = [a.double().requires_grad_(True) for a in arch0]
+    v64 = (valid[0].double(), valid[1], valid[2])
+    g64 = O.arch_grad_first_order(P64, O.BNState(B64), a64, v64, dropout_p=0.0)
+    g32 = dbg_a["dalpha"] if unrolled else g
+    yard = [rel_err(x, y) for x, y in zip(g32, g64)]
     loss = O.w_step(par, bns, arch, train, {}, keys, debug=dbg_w, dropout_p=0.0)
     res = dict(init=init, arch0=arch0, train=train, valid=valid, keys=keys, darch=[t.detach() for t in g],
                arch_after=arch_after, loss=loss, wgrads=[t * dbg_w["clip_coef"] for t in dbg_w["grads"]],
-               total_norm=dbg_w["total_norm"], warch=dbg_w["arch_grads"], buf_after={k: v.clone() for k, v in bns.state.items()}, dbg=dbg_a)
+               total_norm=dbg_w["total_norm"], warch=dbg_w["arch_grads"], yard=yard, buf_after={k: v.clone() for k, v in bns.state.items()}, dbg=dbg_a)
     _FULL_CACHE[key] = res
     return res
 
@@ -624,7 +639,7 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
     else:
         step.alpha_step(train, valid, 1e-3, unrolled=unrolled)
         for i, a in enumerate(m.arch_parameters()):           # the alpha-step's own gradient, before the w-step adds to .grad
-            assert_close(a.grad, ref["darch"][i], REL_TOL, f"alpha-step darch{i}")
+            assert_close(a.grad, ref["darch"][i], max(REL_TOL, 3.0 * ref["yard"][i]), f"alpha-step darch{i}")
         loss = step.w_step(*train)
     report = {}
     # ---- alpha-step ----
@@ -636,17 +651,18 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
         R = float(L["R"])
         gmax = 0.0
         for i in range(4):
-            assert_close(L["g_pos"][i], d["g_pos"][i], REL_TOL, f"g+[{i}]")
-            assert_close(L["g_neg"][i], d["g_neg"][i], REL_TOL, f"g-[{i}]")
+            tol_i = max(REL_TOL, 3.0 * ref["yard"][i])      # same kind of quantity as the yardstick gradient
+            assert_close(L["g_pos"][i], d["g_pos"][i], tol_i, f"g+[{i}]")
+            assert_close(L["g_neg"][i], d["g_neg"][i], tol_i, f"g-[{i}]")
             gmax = max(gmax, float(d["g_pos"][i].abs().max()) + float(d["g_neg"][i].abs().max()))
         for i in range(4):       # raw finite difference: cancellation-aware bound
             hv = (L["g_pos"][i] - L["g_neg"][i]).cpu() / (2 * R)
             hr = (d["g_pos"][i] - d["g_neg"][i]) / (2 * R_ref)
-            assert (hv - hr).abs().max().item() <= REL_TOL * gmax / (2 * R_ref), f"hvp[{i}]"
+            assert (hv - hr).abs().max().item() <= max(REL_TOL, 3.0 * ref["yard"][i]) * gmax / (2 * R_ref), f"hvp[{i}]"
     for i, a in enumerate(m.arch_parameters()):
         # .grad holds the alpha-step's gradient PLUS what the w-step's loss.backward() accumulated on top of it
         # (experiment.py:195 does the same in the reference; the next alpha-step zeroes it)
-        assert_close(a.grad, ref["darch"][i] + ref["warch"][i], REL_TOL, f"darch{i}")
+        assert_close(a.grad, ref["darch"][i] + ref["warch"][i], max(REL_TOL, 6.0 * ref["yard"][i]), f"darch{i}")
         assert_close(a.detach(), ref["arch_after"][i], 1e-5, f"arch_after{i}")
     # ---- w-step ----
     assert_close(loss, ref["loss"], 1e-5, "w-step loss")
@@ -673,5 +689,6 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
     for k in ("img_encoder.darts.stem.1.running_mean", "img_encoder.darts.stem.1.running_var",
               "img_encoder.darts.cells.3._ops.13._ops.5.op.7.running_var", "img_encoder.darts.cells.1.preprocess1.op.2.running_mean"):
         assert_close(sd[k], ref["buf_after"][k], 1e-5, k)
-    report.update(worst_wgrad=worst, wgrads_within=within)
+    report.update(worst_wgrad=worst, wgrads_within=within, oracle32_vs_fp64_darch=ref["yard"],
+                  ours_vs_oracle32_darch=[rel_err(a.grad, ref["darch"][i] + ref["warch"][i]) for i, a in enumerate(m.arch_parameters())])
     return report

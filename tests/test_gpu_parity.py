@@ -177,9 +177,7 @@ def _graph_pair(unrolled):
     batches = [(P.vqa_batch(31, DEV), P.vqa_batch(32, DEV)), (P.vqa_batch(41, DEV), P.vqa_batch(42, DEV))]
     m1, eager = make()
     m2, st = make()
-    graphed = GraphedSearchStep(st, *batches[0], 1e-3, unrolled=unrolled, warmup=2)
-    for _ in range(2):
-        eager.step(*batches[0], 1e-3, unrolled=unrolled)
+    graphed = GraphedSearchStep(st, *batches[0], 1e-3, unrolled=unrolled, warmup=2)      # the warm-up steps are undone
     return m1, eager, m2, graphed, batches
 
 
