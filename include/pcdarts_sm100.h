@@ -113,6 +113,10 @@ typedef struct pcd_cell_fwd_args {
     float* out;               /* (B, 4C, Ho, Wo) contiguous */
     float* saved;             /* saved arena */
     double* stats;            /* stats arena (zeroed by the call) */
+    int32_t skip_dw_outputs;  /* 1: the backward of this forward will not ask for parameter gradients (the two
+                                 finite-difference passes of the Hessian-vector product, architect_vqa.py:109,114): the
+                                 saved depthwise outputs, which only the weight-gradient jobs read, are not written
+                                 (pcd_cell_backward must then be called with need_param_grads == 0).  0: everything saved */
 } pcd_cell_fwd_args;
 
 int pcd_cell_forward(const pcd_cell_fwd_args* a, void* stream);

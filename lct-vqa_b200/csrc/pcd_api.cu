@@ -6,6 +6,7 @@
 // arithmetic, never a product path (pcd_is_cuda_build() returns 0 there and the product loader refuses it).
 #include "pcd_bwd.cuh"
 #include "pcd_pre.cuh"
+#include "pcd_edge_v4.cuh"
 #include "pcd_kernels.h"
 #include "pcd_launch.cuh"
 
@@ -109,7 +110,7 @@ static bool fast_ok(const EdgeGeom& q, const Tile& t, bool stageB) {
            q.Hs == q.S * q.Ho && q.Ws % 4 == 0;
 }
 
-static int run_passAB(const EdgeGeom& q, const EdgeF* edges, int n, float eps, void* stream) {
+static int run_passAB(const EdgeGeom& q, const EdgeF* edges, int n, float eps, int save_t, void* stream) {
     if (n == 0) return PCD_OK;
     if (n > kMaxEdgesPerLaunch) return PCD_ERR_ARG;
     PassArgs a;
@@ -119,6 +120,16 @@ static int run_passAB(const EdgeGeom& q, const EdgeF* edges, int n, float eps, v
     for (int i = 0; i < n; ++i) {
         a.e[i] = edges[i];
         al = al && aligned16(edges[i].x) && aligned16(edges[i].saved) && edges[i].x_ns % 4 == 0;
+    }
+    // production geometries: the v4 kernels (one block runs every stage-A job from one staged tile)
+    bool al4 = al;
+    for (int i = 0; i < n; ++i) al4 = al4 && aligned16(edges[i].par);
+    if (al4 && q.Hs == q.S * q.Ho && q.Ws == q.S * q.Wo && fwd4_supported(q.c, q.S, q.Ho, q.Wo) && !getenv("PCD_NO_V4")) {
+        FwdV4Args v;
+        memset(&v, 0, sizeof v);
+        v.B = q.B; v.Hs = q.Hs; v.Ws = q.Ws; v.Ho = q.Ho; v.Wo = q.Wo; v.eps = eps; v.nedges = n; v.save_t = save_t; v.jobs = 1;
+        for (int i = 0; i < n; ++i) v.e[i] = edges[i];
+        return launch_fwd4(v, q.c, q.S, stream);
     }
     Tile t = pick_tile(q.Ho, q.Wo, q.c, q.S == 1 ? 4096 : 2048);
     a.TH = t.TH; a.TW = t.TW; a.tiles_x = t.tiles_x;
@@ -478,7 +489,7 @@ int pcd_cell_forward(const pcd_cell_fwd_args* a, void* stream) {
             ++n;
         }
         q.Ho = L.Ho; q.Wo = L.Wo;
-        PCD_TRY(run_passAB(q, ef, n, eps, stream));
+        PCD_TRY(run_passAB(q, ef, n, eps, a->skip_dw_outputs ? 0 : 1, stream));
         EdgeC ec[kMaxNodeIn];
         const int e0 = L.first_edge[w];
         for (int j = 0; j < 2 + w; ++j) {
@@ -672,7 +683,7 @@ int pcd_mixedop_forward(const pcd_mixedop_fwd_args* a, void* stream) {
     PCD_TRY(zero_async(a->stats, edge_stats_doubles(q.c, q.S) * sizeof(double), stream));
     EdgeF ef;
     ef.x = a->x; ef.x_ns = C * q.Hs * q.Ws; ef.par = a->params; ef.saved = a->saved; ef.stats = a->stats;
-    PCD_TRY(run_passAB(q, &ef, 1, a->shape.bn_eps, stream));
+    PCD_TRY(run_passAB(q, &ef, 1, a->shape.bn_eps, 1, stream));
     EdgeC ec;
     memset(&ec, 0, sizeof ec);
     ec.x = a->x; ec.x_ns = ef.x_ns; ec.stride = q.S; ec.Hs = q.Hs; ec.Ws = q.Ws; ec.saved = a->saved; ec.stats = a->stats;

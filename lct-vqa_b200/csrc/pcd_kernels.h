@@ -15,6 +15,10 @@ bool bwd2_tile(int c, int S, int Ho, int Wo, int* TH);
 int launch_bwdB2(const EdgeBwdArgs& a, int c, int gz, void* stream);
 int launch_bwdA2(const EdgeBwdArgs& a, int c, int gz, void* stream);
 int launch_wgrad2(const EdgeBwdArgs& a, int c, int gz, void* stream);
+// v4 forward (pcd_edge_v4.cuh): stage A + stage B of a group of production-geometry edges
+struct FwdV4Args;
+bool fwd4_supported(int c, int S, int Ho, int Wo);
+int launch_fwd4(const FwdV4Args& a, int c, int S, void* stream);
 struct PreArgs;
 struct PreBwdArgs;
 int launch_pre_conv(const PreArgs& a, void* stream);

@@ -32,7 +32,8 @@ class CellSizes(C.Structure):
 
 class CellFwdArgs(C.Structure):
     _fields_ = [("shape", CellShape)] + [(n, vp) for n in ("s0", "s1", "weights", "weights2", "params", "running",
-                                                           "nbt", "out", "saved", "stats")]
+                                                           "nbt", "out", "saved", "stats")] + \
+        [("skip_dw_outputs", i32)]
 
 
 class CellBwdArgs(C.Structure):

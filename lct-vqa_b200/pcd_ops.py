@@ -220,8 +220,10 @@ class CellFunction(torch.autograd.Function):
         out = _empty((B, 4 * handle.cfg[2], sz.out_height, sz.out_width), torch.float32, dev)
         saved = _empty(sz.saved_floats, torch.float32, dev)
         stats = _empty(sz.stats_doubles, torch.float64, dev)
+        # activation-only passes (no parameter takes part in autograd) never run the weight-grad jobs: skip what only they read
+        skip_t = int(not any(ctx.needs_input_grad[5:]))
         a = N.CellFwdArgs(handle.shape(B, H, W), N.ptr(s0c), N.ptr(s1c), N.ptr(w), N.ptr(w2), handle.param_ptr,
-                          handle.running_ptr, handle.nbt_ptr, N.ptr(out), N.ptr(saved), N.ptr(stats))
+                          handle.running_ptr, handle.nbt_ptr, N.ptr(out), N.ptr(saved), N.ptr(stats), skip_t)
         N.check(lib, lib.pcd_cell_forward(C.byref(a), N.stream_for(s1c)), "pcd_cell_forward")
         ctx.handle, ctx.params, ctx.geom = handle, params, (B, H, W)
         ctx.save_for_backward(s0c, s1c, w, w2, out, saved, stats)

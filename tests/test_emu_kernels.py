@@ -29,7 +29,10 @@ def test_cell_emulated(name, cpp, cp, C, red, rp):
 
 # production tile geometries (compile-time-tile "FAST" specialisations), one image each
 @pytest.mark.parametrize("C,stride,B,H", [(16, 1, 1, 64), (32, 2, 1, 64), (32, 1, 2, 32), (64, 2, 1, 32), (64, 1, 2, 16)])
-def test_mixed_op_fixed_tiles_emulated(C, stride, B, H):
+@pytest.mark.parametrize("jobs", ["1", "2"])
+def test_mixed_op_fixed_tiles_emulated(C, stride, B, H, jobs, monkeypatch):
+    # v4 forward kernels: one block runs every stage-A job (large waves) | jobs split over two blocks (small waves)
+    monkeypatch.setenv("PCD_V4_JOBS", jobs)
     P.mixed_vs_oracle(C, stride, B, H, "cpu")
 
 

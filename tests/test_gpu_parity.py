@@ -37,7 +37,11 @@ def test_shuffle_bit_exact():
 
 # the five production edge shapes of SURVEY.md §8(a) at a batch the oracle finishes in seconds
 @pytest.mark.parametrize("C,stride,B,H", [(16, 1, 4, 64), (32, 2, 4, 64), (32, 1, 4, 32), (64, 2, 4, 32), (64, 1, 8, 16)])
-def test_mixed_op_production_shapes_vs_oracle(C, stride, B, H):
+@pytest.mark.parametrize("jobs", ["auto", "1", "2"])
+def test_mixed_op_production_shapes_vs_oracle(C, stride, B, H, jobs, monkeypatch):
+    # jobs: the v4 forward kernels' two block layouts (all stage-A jobs in one block | split over two), forced either way
+    if jobs != "auto":
+        monkeypatch.setenv("PCD_V4_JOBS", jobs)
     P.mixed_vs_oracle(C, stride, B, H, DEV)
 
 
