@@ -7,6 +7,7 @@
 #include "pcd_bwd.cuh"
 #include "pcd_pre.cuh"
 #include "pcd_edge_v4.cuh"
+#include "pcd_edge_bwd4.cuh"
 #include "pcd_kernels.h"
 #include "pcd_launch.cuh"
 
@@ -185,6 +186,11 @@ static bool edge_bwd_is_v3(const EdgeGeom& q) {
            bwd2_tile(q.c, 1, q.Ho, q.Wo, &thB);
 }
 
+// v4 stage-A data kernels (plain stores into the partial-grad slots: no memset, no reductions)
+static bool edge_bwd_is_v4(const EdgeGeom& q) {
+    return edge_bwd_is_v3(q) && fwd4_supported(q.c, q.S, q.Ho, q.Wo) && !getenv("PCD_NO_V4");
+}
+
 // v3 weight-gradient jobs for edges whose data jobs already ran (any number of edges, one stride)
 static int run_edge_wgrad2(const EdgeGeom& q, const EdgeG* edges, int n, float eps, void* stream) {
     int thA = 0;
@@ -219,10 +225,15 @@ static int run_edge_bwd(const EdgeGeom& q, const EdgeG* edges, int n, float eps,
         bwd2_tile(q.c, 1, q.Ho, q.Wo, &thB);
         a.need_wgrad = 0;
         a.TH = thB; a.TW = q.Wo; a.tiles_x = 1;
-        if (merged) *merged = 1;         // edges[i].pd: two zeroed slots accumulated with reductions (caller's job)
         PCD_TRY(launch_bwdB2(a, q.c, n * 2, stream));
         a.TH = thA;
-        PCD_TRY(launch_bwdA2(a, q.c, n * bwdA_njobs(q.S), stream));
+        if (edge_bwd_is_v4(q)) {
+            if (merged) *merged = 2;     // edges[i].pd: two slots written with plain stores, ReLU mask already applied to slot 0
+            PCD_TRY(launch_bwdA4(a, q.c, n, stream));
+        } else {
+            if (merged) *merged = 1;     // edges[i].pd: two zeroed slots accumulated with reductions (caller's job)
+            PCD_TRY(launch_bwdA2(a, q.c, n * bwdA_njobs(q.S), stream));
+        }
         if (need_wgrad) {
             if (defer) *defer = 1;
             else PCD_TRY(run_edge_wgrad2(q, edges, n, eps, stream));
@@ -521,7 +532,16 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
     const long long node = (long long)L.B * L.C * L.Ho * L.Wo;
     PCD_TRY(zero_async(a->bstats, L.tot.bwd_stats_doubles * sizeof(double), stream));
     if (a->need_param_grads) PCD_TRY(zero_async(a->grad_params, L.tot.param_floats * sizeof(float), stream));
-    PCD_TRY(zero_async(a->work + L.pd2_begin, L.pd2_floats * sizeof(float), stream));      // merged partial-grad slots
+    {   // merged partial-grad slots: the v3 data kernels accumulate into them (zero first); the v4 kernels store
+        bool all_v4 = true;
+        for (int e = 0; e < PCD_MAX_EDGES; ++e) {
+            StateRef s = state_ref(L, a->saved, a->out, L.src_of[e]);
+            EdgeGeom q;
+            q.B = L.B; q.c = L.c; q.S = L.stride[e]; q.Hs = s.H; q.Ws = s.W; q.Ho = L.Ho; q.Wo = L.Wo;
+            all_v4 = all_v4 && edge_bwd_is_v4(q);
+        }
+        if (!all_v4) PCD_TRY(zero_async(a->work + L.pd2_begin, L.pd2_floats * sizeof(float), stream));
+    }
     auto dn_ptr = [&](int i, long long& ns) -> const float* {
         if (i == 3) { ns = 4 * (node / L.B); return a->grad_out + 3 * (node / L.B); }
         ns = node / L.B;
@@ -711,7 +731,7 @@ int pcd_mixedop_backward(const pcd_mixedop_bwd_args* a, void* stream) {
     eg.bstats = a->bstats; eg.par = a->params; eg.gpar = a->need_param_grads ? a->grad_params : nullptr;
     eg.alpha = a->weights; eg.beta = nullptr; eg.ga = a->work; eg.pd = a->work + 2 * q.nslot();
     int merged = 0;
-    if (edge_bwd_is_v3(q)) PCD_TRY(zero_async(eg.pd, (size_t)2 * q.B * q.c * q.Hs * q.Ws * sizeof(float), stream));
+    if (edge_bwd_is_v3(q) && !edge_bwd_is_v4(q)) PCD_TRY(zero_async(eg.pd, (size_t)2 * q.B * q.c * q.Hs * q.Ws * sizeof(float), stream));
     PCD_TRY(run_edge_bwd(q, &eg, 1, a->shape.bn_eps, a->need_param_grads, stream, nullptr, &merged));
     SourceGradArgs sg;
     memset(&sg, 0, sizeof sg);

@@ -155,6 +155,7 @@ struct SrcEdge {
     const float* beta;     // null => 1
     int stride;
     int merged;            // 1: slot 0 = sum of the pre-mask partials (A3 A5 D3 D5 FR), slot 1 = max-pool + avg-pool(+identity)
+                           // 2: the same two slots, the ReLU mask already applied to slot 0 by its producer (v4 backward)
 };
 
 constexpr int kMaxSrcEdges = 4;
@@ -209,10 +210,11 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
 #pragma unroll
             for (int k = 0; k < kMaxSrcEdges; ++k)
                 if (k < a.nedges) {
-                    v.x += (xv.x > 0.f ? m[k].x : 0.f) + q4[k].x;
-                    v.y += (xv.y > 0.f ? m[k].y : 0.f) + q4[k].y;
-                    v.z += (xv.z > 0.f ? m[k].z : 0.f) + q4[k].z;
-                    v.w += (xv.w > 0.f ? m[k].w : 0.f) + q4[k].w;
+                    const bool pre = a.e[k].merged == 2;        // mask already applied
+                    v.x += ((pre || xv.x > 0.f) ? m[k].x : 0.f) + q4[k].x;
+                    v.y += ((pre || xv.y > 0.f) ? m[k].y : 0.f) + q4[k].y;
+                    v.z += ((pre || xv.z > 0.f) ? m[k].z : 0.f) + q4[k].z;
+                    v.w += ((pre || xv.w > 0.f) ? m[k].w : 0.f) + q4[k].w;
                 }
             *reinterpret_cast<F4*>(a.out + (long long)n * a.out_ns + (long long)ch * HW + p) = v;
         }
@@ -233,10 +235,11 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
                 const float* pd = e.pd + ((long long)n * c + ch) * HW + p;
                 if (e.merged) {
                     const F4 m = *reinterpret_cast<const F4*>(pd), q4 = *reinterpret_cast<const F4*>(pd + pslot);
-                    v.x += (xv.x > 0.f ? m.x : 0.f) + q4.x;
-                    v.y += (xv.y > 0.f ? m.y : 0.f) + q4.y;
-                    v.z += (xv.z > 0.f ? m.z : 0.f) + q4.z;
-                    v.w += (xv.w > 0.f ? m.w : 0.f) + q4.w;
+                    const bool pre = e.merged == 2;
+                    v.x += ((pre || xv.x > 0.f) ? m.x : 0.f) + q4.x;
+                    v.y += ((pre || xv.y > 0.f) ? m.y : 0.f) + q4.y;
+                    v.z += ((pre || xv.z > 0.f) ? m.z : 0.f) + q4.z;
+                    v.w += ((pre || xv.w > 0.f) ? m.w : 0.f) + q4.w;
                     continue;
                 }
                 F4 m = {0.f, 0.f, 0.f, 0.f};
@@ -339,7 +342,7 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
             if (ch < c) {
                 const float* pd = e.pd + ((long long)n * c + ch) * HW + p;
                 if (e.merged) {
-                    v += (xb[p] > 0.f ? pd[0] : 0.f) + pd[pslot];
+                    v += ((e.merged == 2 || xb[p] > 0.f) ? pd[0] : 0.f) + pd[pslot];
                     continue;
                 }
                 float m = pd[0] + pd[pslot] + pd[2 * pslot] + pd[3 * pslot];

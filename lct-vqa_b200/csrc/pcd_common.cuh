@@ -42,9 +42,11 @@ constexpr int kThreads = 256;
 #if PCD_CUDA
 #define PCD_TSTATE(type, name, dims) type name dims
 #define PCD_TREF(name, tid) name
+#define PCD_TPASS(name) name                    // the whole state, as a function argument / parameter name
 #else
 #define PCD_TSTATE(type, name, dims) type name##_all[pcd::kThreads] dims
 #define PCD_TREF(name, tid) name##_all[tid]
+#define PCD_TPASS(name) name##_all
 #endif
 #define PCD_EACH(task) PCD_FOR(task, pcd::kThreads)
 

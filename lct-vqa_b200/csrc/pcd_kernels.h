@@ -19,6 +19,8 @@ int launch_wgrad2(const EdgeBwdArgs& a, int c, int gz, void* stream);
 struct FwdV4Args;
 bool fwd4_supported(int c, int S, int Ho, int Wo);
 int launch_fwd4(const FwdV4Args& a, int c, int S, void* stream);
+// v4 stage-A backward data kernels (pcd_edge_bwd4.cuh): plain stores into the two partial-grad slots of every edge
+int launch_bwdA4(const EdgeBwdArgs& a, int c, int nedges, void* stream);
 struct PreArgs;
 struct PreBwdArgs;
 int launch_pre_conv(const PreArgs& a, void* stream);
