@@ -45,14 +45,20 @@ class _TrainingState:
     at them.  Used to undo the warm-up steps a graph capture needs: construction must not consume training steps."""
 
     def __init__(self, modules, arch_tensors, optimizers):
-        self.tensors = []
+        # hold the parameter / buffer OBJECTS, not their .data: the first forward pass re-binds .data to views of one
+        # flat arena (pcd_ops.Arena), and the values must go back into whatever storage is live at restore time
+        self.holders = []
         for m in modules:
-            self.tensors += [p.data for p in m.parameters()] + list(m.buffers())
-        self.tensors += [a.data for a in arch_tensors]
-        self.saved = [t.clone() for t in self.tensors]
+            self.holders += list(m.parameters()) + list(m.buffers())
+        self.holders += list(arch_tensors)
+        self.saved = [t.detach().clone() for t in self.holders]
         self.optimizers = list(optimizers)
         self.opt_saved = [{id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
                            for p, st in opt.state.items()} for opt in self.optimizers]
+
+    @property
+    def tensors(self):
+        return [t.data for t in self.holders]
 
     def restore(self):
         with torch.no_grad():

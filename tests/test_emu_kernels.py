@@ -178,3 +178,21 @@ def test_graph_warmup_state_is_restored():
     assert int(bn.num_batches_tracked) == 0
     for st in opt.state.values():
         assert float(st["step"]) == 0 and float(st["exp_avg"].abs().max()) == 0 and float(st["exp_avg_sq"].abs().max()) == 0
+
+
+def test_graph_warmup_restore_survives_arena_rebinding():
+    """The first forward re-binds every parameter's .data to a view of the flat arena (pcd_ops.Arena); a snapshot taken
+    before it must still restore into the live storage (found on the GPU: the graph used to start two steps late)."""
+    from search import _TrainingState
+    m = P.make_vqa("cpu")
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    snap = _TrainingState([m], m.arch_parameters(), [opt])
+    before = [p.detach().clone() for p in m.parameters()]
+    ptr_before = next(iter(m.img_encoder.darts.cells.parameters())).data_ptr()
+    img, qst, lbl = P.vqa_batch(11, "cpu")
+    m._loss(img, qst, lbl).backward()
+    opt.step()
+    assert next(iter(m.img_encoder.darts.cells.parameters())).data_ptr() != ptr_before      # storage was re-bound
+    assert any(not torch.equal(a, b) for a, b in zip(m.parameters(), before))
+    snap.restore()
+    assert all(torch.equal(a.detach(), b) for a, b in zip(m.parameters(), before))
