@@ -201,8 +201,10 @@ def shuffle_case(device):
     assert torch.equal(x.grad.cpu(), ref.grad)
 
 
-def mixed_vs_oracle(C, stride, B, H, device, seed=7, check_grads=True):
-    """Larger shapes than the goldens: product on `device` vs the oracle on CPU, same seeded inputs."""
+def mixed_vs_oracle(C, stride, B, H, device, seed=7, check_grads=True, quantized=False):
+    """Larger shapes than the goldens: product on `device` vs the oracle on CPU, same seeded inputs.
+    quantized: the input only takes multiples of 0.5, so 3x3 / 2x2 max-pool windows are full of exact ties (ATen routes the
+    gradient to the FIRST maximum in scan order) and many ReLU inputs are exactly 0 (gradient 0)."""
     import config
     config.DEVICE = device
     from pcdarts.model_search import MixedOp
@@ -214,6 +216,8 @@ def mixed_vs_oracle(C, stride, B, H, device, seed=7, check_grads=True):
         v.requires_grad_(True)
     gen = torch.Generator().manual_seed(seed)
     x = torch.randn(B, C, H, H, generator=gen)
+    if quantized:
+        x = torch.round(2 * x) / 2
     w = torch.softmax(torch.randn(8, generator=gen), 0)
     G = torch.randn(B, C, H // stride, H // stride, generator=gen)
     xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)

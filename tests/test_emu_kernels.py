@@ -36,6 +36,12 @@ def test_mixed_op_fixed_tiles_emulated(C, stride, B, H, jobs, monkeypatch):
     P.mixed_vs_oracle(C, stride, B, H, "cpu")
 
 
+@pytest.mark.parametrize("C,stride,B,H", [(16, 1, 1, 64), (32, 2, 1, 64), (64, 2, 1, 32), (64, 1, 2, 16)])
+def test_mixed_op_exact_ties_emulated(C, stride, B, H):
+    """Max-pool windows full of exact ties, ReLU inputs exactly 0: first-maximum routing / zero sub-gradient as in ATen."""
+    P.mixed_vs_oracle(C, stride, B, H, "cpu", quantized=True)
+
+
 # preprocess 1x1 GEMM kernels: ragged pixel tiles, FactorizedReduce (fast and generic loads), partial channel chunks
 @pytest.mark.parametrize("c_in,c_out,fr,B,H", [(48, 16, False, 2, 16), (48, 32, False, 1, 20), (64, 64, True, 2, 16),
                                                  (128, 64, False, 1, 18), (64, 32, True, 1, 12), (40, 16, False, 1, 9),

@@ -45,6 +45,13 @@ def test_mixed_op_production_shapes_vs_oracle(C, stride, B, H, jobs, monkeypatch
     P.mixed_vs_oracle(C, stride, B, H, DEV)
 
 
+@pytest.mark.parametrize("C,stride,B,H", [(16, 1, 4, 64), (32, 2, 4, 64), (32, 1, 4, 32), (64, 2, 4, 32), (64, 1, 8, 16)])
+def test_mixed_op_exact_ties(C, stride, B, H):
+    """Inputs on a 0.5 grid: 3x3 and 2x2 max-pool windows full of exact ties (ATen routes the gradient to the first maximum
+    in scan order), ReLU inputs exactly 0 (zero sub-gradient)."""
+    P.mixed_vs_oracle(C, stride, B, H, DEV, quantized=True)
+
+
 # the eight production preprocess shapes (SURVEY.md §8a) at reduced batch, plus shapes that make one block loop over
 # several input-channel chunks (many pixel tiles) and shapes that split the chunks over blockIdx.z (few tiles)
 @pytest.mark.parametrize("c_in,c_out,fr,B,H", [
