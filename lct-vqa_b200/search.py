@@ -26,7 +26,7 @@ class SearchStep:
         loss.backward()
         if self.reducer is not None:
             self.reducer([p.grad for p in self._params if p.grad is not None])
-        nn.utils.clip_grad_norm_(self._params, self.grad_clip)
+        self.last_grad_norm = nn.utils.clip_grad_norm_(self._params, self.grad_clip)     # the norm BEFORE clipping
         self.optimizer.step()
         return loss.detach()
 
