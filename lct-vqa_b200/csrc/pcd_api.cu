@@ -267,7 +267,8 @@ static int run_pre_forward(int B, int Cin, int Cout, int Hin, int Win, int fr, f
     a.Ho = fr ? Hin / 2 : Hin; a.Wo = fr ? Win / 2 : Win;
     a.eps = eps; a.momentum = mom; a.x = x; a.w = w; a.y = y; a.stats = stats; a.running = running; a.nbt = nbt;
     const int HW = a.Ho * a.Wo;
-    PCD_TRY(launch_pre_conv(a, stream));
+    if (pre_tc_supported(B, Cin, Cout, Hin, Win, fr) && aligned16(x) && aligned16(w) && aligned16(y)) PCD_TRY(launch_pre_tc_fwd(a, stream));
+    else PCD_TRY(launch_pre_conv(a, stream));
     NormArgs nrm;
     memset(&nrm, 0, sizeof nrm);
     nrm.B = B; nrm.C = Cout; nrm.HW = HW; nrm.eps = eps; nrm.momentum = mom; nrm.src = y; nrm.dst = y;
@@ -289,6 +290,8 @@ static int run_pre_backward(int B, int Cin, int Cout, int Hin, int Win, int fr, 
     a.B = B; a.Cin = Cin; a.Cout = Cout; a.Hin = Hin; a.Win = Win; a.Ho = Ho; a.Wo = Wo; a.fr = fr;
     a.x = x; a.w = w; a.y = y; a.dy = dy; a.stats = stats; a.bstats = bstats; a.eps = eps; a.dx = dx; a.gw = gw;
     a.chunks_per_block = 0;      // chosen by the launcher
+    if (pre_tc_supported(B, Cin, Cout, Hin, Win, fr) && aligned16(x) && aligned16(w) && aligned16(y) && aligned16(dy) && (!dx || aligned16(dx)))
+        return launch_pre_tc_bwd(a, stream);
     return launch_pre_bwd(a, stream);
 }
 

@@ -24,5 +24,9 @@ int launch_bwdA4(const EdgeBwdArgs& a, int c, int nedges, void* stream);
 struct PreArgs;
 struct PreBwdArgs;
 int launch_pre_conv(const PreArgs& a, void* stream);
+// tensor-core (tcgen05) preprocess kernels, pcd_pre_tc.cu: plain 1x1 ReLUConvBN at the production shapes
+bool pre_tc_supported(int B, int Cin, int Cout, int H, int W, int fr);
+int launch_pre_tc_fwd(const PreArgs& a, void* stream);
+int launch_pre_tc_bwd(const PreBwdArgs& a, void* stream);
 int launch_pre_bwd(const PreBwdArgs& a, void* stream);
 }  // namespace pcd

@@ -611,10 +611,21 @@ def _oracle_search_step(unrolled, B, V, img, dims):
     # a pass has a handful of them (measured on the GPU: 3e-3 on d alphas_normal at w - R v, deterministic run to run)
     flips = 3.0 / (B * (img // 4) ** 2 * 16) ** 0.5 if B >= 32 else 0.0
     yard = [max(max(yard), flips / 5.0)] * 4
+    buf_w = {k: v.clone() for k, v in bns.state.items()}
     loss = O.w_step(par, bns, arch, train, {}, keys, debug=dbg_w, dropout_p=0.0)
+    # float64 yardstick for the w-step's weight gradients (same weights, post-Adam alphas, training batch): with a real loss
+    # the search-network gradients are sums with heavy cancellation (BatchNorm makes them orthogonal to the weights), so
+    # the fp32 ORACLE is itself 1e-4 .. 1e-3 away from this on most tensors; ours must not be further away in kind
+    P64w = {k: init[k].double().requires_grad_(True) for k in keys}
+    B64w = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in buf_w.items()}
+    a64w = [a.detach().double() for a in arch_after]
+    l64 = O.vqa_loss(P64w, O.BNState(B64w), a64w, train[0].double(), train[1], train[2], dropout_p=0.0)
+    w64 = torch.autograd.grad(l64, [P64w[k] for k in keys], allow_unused=True)
+    wgrads64 = [torch.zeros_like(P64w[k]) if g is None else g for g, k in zip(w64, keys)]
     res = dict(init=init, arch0=arch0, train=train, valid=valid, keys=keys, darch=[t.detach() for t in g],
                arch_after=arch_after, loss=loss, wgrads=[t * dbg_w["clip_coef"] for t in dbg_w["grads"]],
-               total_norm=dbg_w["total_norm"], warch=dbg_w["arch_grads"], yard=yard, buf_after={k: v.clone() for k, v in bns.state.items()}, dbg=dbg_a)
+               total_norm=dbg_w["total_norm"], warch=dbg_w["arch_grads"], yard=yard, wgrads64=wgrads64,
+               wgrads32=[t.clone() for t in dbg_w["grads"]], buf_after={k: v.clone() for k, v in bns.state.items()}, dbg=dbg_a)
     _FULL_CACHE[key] = res
     return res
 
@@ -690,7 +701,9 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
     dnorm = abs(float(step.last_grad_norm) - float(ref["total_norm"])) / float(ref["total_norm"])
     assert dnorm <= 2e-3, f"|grad| before clipping: rel err {dnorm:.3e}"
     tol_w = REL_TOL + 1.5 * dnorm
-    for k, gr in zip(ref["keys"], ref["wgrads"]):
+    coef = min(1.0, 5.0 / (float(step.last_grad_norm) + 1e-6))          # undo the clipping for the fp64 comparison
+    e_ours64, e_or64 = [], []
+    for k, gr, g32, g64 in zip(ref["keys"], ref["wgrads"], ref["wgrads32"], ref["wgrads64"]):
         gp = named[k].grad
         if gp is None:
             assert float(gr.abs().max()) == 0.0, k
@@ -699,17 +712,29 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
         if ".darts." in k:
             assert e <= max(floor, tol_w), f"{k}: rel err {e:.3e}"
             errs.append(e)
+            e_ours64.append(rel_err(gp.detach().cpu().double() / coef, g64))
+            e_or64.append(rel_err(g32, g64))
         else:
             assert e <= tol_w, f"{k}: rel err {e:.3e} (tolerance {tol_w:.2e})"
         worst = max(worst, (e, k))
     within = sum(e <= tol_w for e in errs) / max(1, len(errs))
-    assert within >= 0.90, f"only {within:.1%} of the search-network weight grads are within rel {tol_w:.2e}"
+
+    def q(v, f):
+        return sorted(v)[min(len(v) - 1, int(f * len(v)))]
+    yard_w = dict(ours_vs_fp64_median=q(e_ours64, 0.5), oracle32_vs_fp64_median=q(e_or64, 0.5), ours_vs_fp64_q90=q(e_ours64, 0.9),
+                  oracle32_vs_fp64_q90=q(e_or64, 0.9), ours_vs_oracle32_within=within,
+                  oracle32_vs_fp64_within=sum(e <= tol_w for e in e_or64) / len(e_or64),
+                  ours_vs_fp64_within=sum(e <= tol_w for e in e_ours64) / len(e_ours64))
+    # against the float64 truth this implementation is not further away than the fp32 oracle is (median and 90th percentile)
+    assert yard_w["ours_vs_fp64_median"] <= 2.0 * yard_w["oracle32_vs_fp64_median"] + 1e-6, yard_w
+    assert yard_w["ours_vs_fp64_q90"] <= 3.0 * yard_w["oracle32_vs_fp64_q90"] + 1e-5, yard_w
+    assert yard_w["ours_vs_fp64_within"] >= yard_w["oracle32_vs_fp64_within"] - 0.15, yard_w
     sd = m.state_dict()
     nbt = "img_encoder.darts.stem.1.num_batches_tracked"
     assert int(sd[nbt]) == int(ref["buf_after"][nbt]) == (4 if unrolled else 2)
     for k in ("img_encoder.darts.stem.1.running_mean", "img_encoder.darts.stem.1.running_var",
               "img_encoder.darts.cells.3._ops.13._ops.5.op.7.running_var", "img_encoder.darts.cells.1.preprocess1.op.2.running_mean"):
         assert_close(sd[k], ref["buf_after"][k], 1e-5, k)
-    report.update(worst_wgrad=worst, wgrads_within=within, grad_norm_rel_err=dnorm, oracle32_vs_fp64_darch=ref["yard"],
+    report.update(worst_wgrad=worst, wgrads_within=within, grad_norm_rel_err=dnorm, wgrad_yardstick=yard_w, oracle32_vs_fp64_darch=ref["yard"],
                   ours_vs_oracle32_darch=[rel_err(a.grad, ref["darch"][i] + ref["warch"][i]) for i, a in enumerate(m.arch_parameters())])
     return report
