@@ -59,8 +59,10 @@ struct FwdCfg {
     static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
+// one stage per CTA and five CTAs per SM: a tile has only 3..16 k-blocks, so the latency of its TMA -> split -> MMA -> epilogue
+// chain is hidden by the OTHER resident tiles rather than by a deep ring inside the CTA
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreadsTC, 2)
+__global__ void __launch_bounds__(kThreadsTC, 5)
 pre_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, float* __restrict__ z,
                   double* __restrict__ stats, int Cin, int HW, int rows_per_tile) {
     using G = FwdCfg<BN, STAGES>;
@@ -185,7 +187,7 @@ struct DxCfg {
 };
 
 template <int STAGES>
-__global__ void __launch_bounds__(kThreadsTC, 1)
+__global__ void __launch_bounds__(kThreadsTC, 3)
 pre_tc_dx_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW,
                  const float* __restrict__ x, float* __restrict__ dx, const double* __restrict__ stats, const double* __restrict__ bstats,
                  float eps, double cnt, int Cin, int Cout, int HW, int rows_per_tile, uint32_t tmem_cols) {
@@ -318,7 +320,7 @@ struct DwCfg {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreadsTC, 1)
+__global__ void __launch_bounds__(kThreadsTC, BN == 64 ? 1 : 2)
 pre_tc_dw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmY,
                  float* __restrict__ gw, const double* __restrict__ stats, const double* __restrict__ bstats, float eps, double cnt,
                  int Cin, int HW, int kb_per_cta) {
@@ -483,7 +485,7 @@ struct ProfScope {          // per-launch CUDA events of the library's profiler 
 
 template <int BN>
 static int fwd_go(const PreArgs& a, cudaStream_t st) {
-    constexpr int STAGES = 2;
+    constexpr int STAGES = 1;
     using G = FwdCfg<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -501,7 +503,7 @@ static int fwd_go(const PreArgs& a, cudaStream_t st) {
 
 template <int BN>
 static int dw_go(const PreBwdArgs& a, cudaStream_t st) {
-    constexpr int STAGES = 3;
+    constexpr int STAGES = BN == 64 ? 3 : 2;        // C_out <= 32: two CTAs per SM
     using G = DwCfg<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -514,7 +516,7 @@ static int dw_go(const PreBwdArgs& a, cudaStream_t st) {
     PCD_TRY(map_2d(&tdy, a.dy, HW, (long long)a.B * BN, 32, BN, CU_TENSOR_MAP_SWIZZLE_128B));
     PCD_TRY(map_2d(&ty, a.y, HW, (long long)a.B * BN, 32, BN, CU_TENSOR_MAP_SWIZZLE_128B));
     const int mt = (a.Cin + BM - 1) / BM, total_kb = HW / 32;
-    int ksplit = (296 + mt * a.B - 1) / (mt * a.B);              // about two CTAs per SM over the grid
+    int ksplit = (444 + mt * a.B - 1) / (mt * a.B);              // about three CTAs per SM over the grid
     if (ksplit < 1) ksplit = 1;
     if (ksplit > total_kb / 4) ksplit = total_kb / 4 > 0 ? total_kb / 4 : 1;
     const int kbps = (total_kb + ksplit - 1) / ksplit;
@@ -549,7 +551,7 @@ int launch_pre_tc_bwd(const PreBwdArgs& a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = a.Hin * a.Win;
     if (a.dx) {
-        const int stages = (DxCfg<2>::smem(a.Cin, a.Cout) <= 110 * 1024) ? 2 : 1;
+        const int stages = 1;        // occupancy (3-5 CTAs per SM) hides the per-tile latency better than a second stage does
         const size_t sm = stages == 2 ? DxCfg<2>::smem(a.Cin, a.Cout) : DxCfg<1>::smem(a.Cin, a.Cout);
         static bool configured = false;
         if (!configured) {

@@ -28,8 +28,11 @@ _LAST_INSTANCE = None      # debugging aid: the most recently constructed archit
 
 
 class ArchitectLct(object):
-    def __init__(self, ef_model, w_model, ef_optimizer, w_optimizer):
+    def __init__(self, ef_model, w_model, ef_optimizer, w_optimizer, reducer=None):
         global _LAST_INSTANCE
+        # data parallel (not in the reference, which is single-process): every gradient evaluation of the step is averaged
+        # across ranks, so the finite-difference radii R = r / |.| and the final alpha-step are identical on all replicas
+        self.reducer = reducer
         _LAST_INSTANCE = self
         self.ef_model = ef_model
         self.w_model = w_model
@@ -136,6 +139,8 @@ class ArchitectLct(object):
             else:
                 assert grads[i].shape == p.shape
         assert num_zero_grad == exp_zero_grad, (num_zero_grad, exp_zero_grad)
+        if self.reducer is not None:
+            self.reducer(grads)
         self.last.setdefault("calls", []).append((loss.detach(), _concat(grads).norm().detach()))
         return grads
 

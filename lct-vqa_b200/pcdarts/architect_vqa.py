@@ -83,6 +83,15 @@ class Architect(object):
             self._twin.train()
         return self._twin
 
+    def _staged(self, model, batch, params, extra=()):
+        """Data-parallel gradients with the all-reduce overlapped with the image encoder's backward (pcd_dist.staged_grads)."""
+        from pcd_dist import staged_grads
+        loss, grads, g_extra = staged_grads(model, batch, params, self.reducer, self.args.qst_only, extra=extra)
+        missing = sum(g is None for g in grads)
+        assert missing == self.exp_zero_grad, (missing, self.exp_zero_grad)
+        grads = [torch.zeros_like(p) if g is None else g for g, p in zip(grads, params)]
+        return grads, g_extra, loss
+
     def _calc_grad(self, loss, params, exp_zero_grad=0):
         grads = list(torch.autograd.grad(loss, params, allow_unused=True))
         missing = 0
@@ -118,9 +127,12 @@ class Architect(object):
     def _compute_unrolled_model(self, img, qst, label, eta, network_optimizer):
         model = self.model
         params, _ = self._lists(model)
-        loss = model._loss(img, qst, label, self.args.qst_only)
-        grads = self._calc_grad(loss, params, self.exp_zero_grad)
-        self._allreduce(grads)
+        if self.reducer is not None and hasattr(model, "_loss_staged"):
+            grads = self._staged(model, (img, qst, label), params)[0]
+        else:
+            loss = model._loss(img, qst, label, self.args.qst_only)
+            grads = self._calc_grad(loss, params, self.exp_zero_grad)
+            self._allreduce(grads)
         twin = self.unrolled_model()
         with torch.no_grad():
             self._copy_state(twin, model)                                # model_dict carries the live BN buffers
@@ -132,11 +144,15 @@ class Architect(object):
         twin = self._compute_unrolled_model(img_train, qst_train, label_train, eta, network_optimizer)
         tparams = self._lists(twin)[0]
         tarch = twin.arch_parameters()
-        unrolled_loss = twin._loss(img_valid, qst_valid, label_valid, self.args.qst_only)
-        got = torch.autograd.grad(unrolled_loss, list(tarch) + tparams, allow_unused=True)
-        dalpha = [g.clone() for g in got[:len(tarch)]]
-        vector = [torch.zeros_like(p) if g is None else g for g, p in zip(got[len(tarch):], tparams)]
-        self._allreduce(dalpha + vector)
+        if self.reducer is not None and hasattr(twin, "_loss_staged"):
+            vector, extra, unrolled_loss = self._staged(twin, (img_valid, qst_valid, label_valid), tparams, extra=list(tarch))
+            dalpha = [g.clone() for g in extra]
+        else:
+            unrolled_loss = twin._loss(img_valid, qst_valid, label_valid, self.args.qst_only)
+            got = torch.autograd.grad(unrolled_loss, list(tarch) + tparams, allow_unused=True)
+            dalpha = [g.clone() for g in got[:len(tarch)]]
+            vector = [torch.zeros_like(p) if g is None else g for g, p in zip(got[len(tarch):], tparams)]
+            self._allreduce(dalpha + vector)
         implicit = self._hessian_vector_product(vector, img_train, qst_train, label_train)
         with torch.no_grad():
             torch._foreach_add_(dalpha, implicit, alpha=-eta)

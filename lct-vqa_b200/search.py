@@ -22,10 +22,18 @@ class SearchStep:
     def w_step(self, image, question, label):
         """experiment.py:187-200."""
         self.optimizer.zero_grad()
-        loss = self.model._loss(image, question, label, self.qst_only)     # = CE(ans) + CE(qst[:, :-1]) of experiment.py:189-194
-        loss.backward()
-        if self.reducer is not None:
-            self.reducer([p.grad for p in self._params if p.grad is not None])
+        if self.reducer is not None and hasattr(self.model, "_loss_staged"):
+            # data parallel: the backward is cut at the image embedding so that the all-reduce of the question-encoder / head
+            # gradients overlaps the search network's backward (pcd_dist.staged_grads); .grad is set, not accumulated
+            from pcd_dist import staged_grads
+            loss, grads, _ = staged_grads(self.model, (image, question, label), self._params, self.reducer, self.qst_only)
+            for p, g in zip(self._params, grads):
+                p.grad = g
+        else:
+            loss = self.model._loss(image, question, label, self.qst_only)     # = CE(ans) + CE(qst[:, :-1]) of experiment.py:189-194
+            loss.backward()
+            if self.reducer is not None:
+                self.reducer([p.grad for p in self._params if p.grad is not None])
         self.last_grad_norm = nn.utils.clip_grad_norm_(self._params, self.grad_clip)     # the norm BEFORE clipping
         self.optimizer.step()
         return loss.detach()

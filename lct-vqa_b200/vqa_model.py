@@ -178,9 +178,15 @@ class VqaModel(VqaModelBase):
     def _loss(self, images, questions, labels, qst_only=False):
         """vqa_model.py:351-364; same value and gradients as CE on `self(images, questions)`, but the question logits stay
         inside the fused projection + cross-entropy op."""
+        return self._loss_staged(images, questions, labels, qst_only)[0]
+
+    def _loss_staged(self, images, questions, labels, qst_only=False):
+        """(loss, image embedding): the embedding is the only tensor through which the loss depends on the image encoder, so
+        a data-parallel backward can be cut there (pcd_dist.staged_grads: the all-reduce of the question-encoder / head
+        gradients runs while the search network's backward is still computing)."""
         img_feature = self.img_encoder(images)
         qst_feature, states = self.qst_encoder(questions, img_feature, return_states=True)
         qst_loss = self.qst_encoder.next_word_loss(states, questions)
         if qst_only:
-            return qst_loss
-        return self.criterion(self._answer(img_feature, qst_feature), labels) + qst_loss
+            return qst_loss, img_feature
+        return self.criterion(self._answer(img_feature, qst_feature), labels) + qst_loss, img_feature

@@ -112,3 +112,33 @@ def _worker_wstep(rank, world, port, out_dir):
         torch.save({"grads": [g.clone() for g in gs]}, os.path.join(out_dir, "w_rank0.pt"))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _worker_lct(rank, world, port, out_dir):
+    _setup()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import parity_cases as P
+    import pcd_dist
+    pcd_dist.init_from_env("gloo")
+    reducer = pcd_dist.GradReducer()
+    ef, w, arch = P.make_lct("cpu")
+    arch.reducer = reducer                      # what get_architect(..., reducer=) sets
+    arch.step(*P.lct_batch(300 + rank, "cpu"), *P.lct_batch(400 + rank, "cpu"), 1e-3, 1e-3)
+    torch.save({"arch": [a.detach().clone() for a in ef.arch_parameters()], "grads": [a.grad.clone() for a in ef.arch_parameters()],
+                "calls": reducer.calls}, os.path.join(out_dir, f"lct_rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_architect_lct_replicas_stay_identical(tmp_path):
+    """ArchitectLct under data parallelism (BASELINE configs[3] for the 3-stage system): every gradient evaluation of the
+    step is averaged, so both ranks — fed different shards — end with bit-identical alpha / beta gradients and alphas."""
+    _setup()
+    port = _free_port()
+    mp.spawn(_worker_lct, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "lct_rank0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "lct_rank1.pt"))
+    assert r0["calls"] == r1["calls"] and r0["calls"] >= 7          # the seven gradient evaluations of architect_lct.py:32-92
+    for a, b in zip(r0["grads"] + r0["arch"], r1["grads"] + r1["arch"]):
+        assert torch.equal(a, b)
+    assert all(torch.isfinite(g).all() and float(g.abs().max()) > 0 for g in r0["grads"])
