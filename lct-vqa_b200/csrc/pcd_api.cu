@@ -267,7 +267,15 @@ static int run_pre_forward(int B, int Cin, int Cout, int Hin, int Win, int fr, f
     a.Ho = fr ? Hin / 2 : Hin; a.Wo = fr ? Win / 2 : Win;
     a.eps = eps; a.momentum = mom; a.x = x; a.w = w; a.y = y; a.stats = stats; a.running = running; a.nbt = nbt;
     const int HW = a.Ho * a.Wo;
-    if (pre_tc_supported(B, Cin, Cout, Hin, Win, fr) && aligned16(x) && aligned16(w) && aligned16(y)) PCD_TRY(launch_pre_tc_fwd(a, stream));
+    // The tcgen05 forward exists and is accurate as an op (y within 6e-7..1.4e-6 of a float64 evaluation, the FP32-FMA
+    // kernel 3e-7..7e-7: tests/test_gpu_parity.py::test_preprocess_tensor_core_path_full_batch), but the search network's
+    // weight gradients amplify forward rounding noise ~100x (cancellation behind BatchNorm): with it, 163 of 714 weight-grad
+    // tensors of the full-size network miss rel 1e-4 against float64 instead of 27 (profiles/r02_pre_tc_parity_ab.txt).
+    // Parity comes first: the forward stays on the FP32-FMA kernel unless PCD_PRE_TC_FWD=1; the two backward products,
+    // whose rounding noise is not amplified, run on the tensor cores.
+    const char* tcf = getenv("PCD_PRE_TC_FWD");
+    if (tcf && tcf[0] == '1' && pre_tc_supported(B, Cin, Cout, Hin, Win, fr) && aligned16(x) && aligned16(w) && aligned16(y))
+        PCD_TRY(launch_pre_tc_fwd(a, stream));
     else PCD_TRY(launch_pre_conv(a, stream));
     NormArgs nrm;
     memset(&nrm, 0, sizeof nrm);

@@ -62,6 +62,45 @@ def test_preprocess_vs_oracle(c_in, c_out, fr, B, H):
     P.pre_vs_oracle(c_in, c_out, fr, B, H, DEV)
 
 
+@pytest.mark.parametrize("c_in,c_out,H", [(48, 16, 64), (48, 32, 64), (64, 32, 64), (128, 64, 32), (256, 64, 16)])
+def test_preprocess_tensor_core_path_full_batch(c_in, c_out, H, monkeypatch):
+    """The tcgen05 preprocess kernels at the production shapes and FULL batch (64) against a float64 evaluation on the GPU,
+    next to the FP32-FMA kernels (PCD_NO_PRE_TC=1) on the same tensors: there are no ReLU / max-pool decisions inside this
+    op's backward and its forward ReLU acts on the given input, so no tie flips to excuse — plain rel 2e-5 (3xTF32)."""
+    import config
+    import torch.nn.functional as F
+    config.DEVICE = DEV
+    from pcdarts.operations import ReLUConvBN
+    torch.manual_seed(c_in + c_out + H)
+    m = ReLUConvBN(c_in, c_out, 1, 1, 0, affine=False).to(DEV).train()
+    x = torch.randn(64, c_in, H, H, device=DEV)
+    G = torch.randn(64, c_out, H, H, device=DEV)
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        m.zero_grad()
+        y = m(xx)
+        (y * G).sum().backward()
+        return y.detach().clone(), xx.grad.clone(), m.op[1].weight.grad.clone()
+    monkeypatch.setenv("PCD_PRE_TC_FWD", "1")          # the forward kernel is opt-in (see run_pre_forward in pcd_api.cu)
+    xd = x.double().requires_grad_(True)
+    wd = m.op[1].weight.detach().double().requires_grad_(True)
+    yd = F.batch_norm(F.conv2d(F.relu(xd), wd), None, None, training=True, eps=1e-5)
+    (yd * G.double()).sum().backward()
+    ref = (yd.detach(), xd.grad, wd.grad)
+    got = run()
+    again = run()
+    monkeypatch.setenv("PCD_NO_PRE_TC", "1")
+    fma = run()
+    rep = {}
+    for name, r, a_, b_, c_ in zip(("y", "dx", "dW"), ref, got, again, fma):
+        rep[name] = dict(tc_vs_fp64=P.rel_err(a_, r), fma_vs_fp64=P.rel_err(c_, r), tc_run_to_run=P.rel_err(b_, a_))
+    print("preprocess tc vs fma vs fp64:", rep)
+    for name, v in rep.items():
+        assert v["tc_run_to_run"] <= 2e-6, (name, rep)          # only the order of the statistics / dW atomics may differ
+        assert v["tc_vs_fp64"] <= 2e-5, (name, rep)
+
+
 # the four production cells (C=16@64, reduce C=32 64->32, reduce C=64 32->16, C=64@16) at batch 2: v3 backward kernels
 # with the cell-wide deferred weight-gradient launch; once more with frozen weights (activation-only backward, HVP passes)
 @pytest.mark.parametrize("cpp,cp,C,red,rp,H", [(48, 48, 16, False, False, 64), (48, 64, 32, True, False, 64),
