@@ -251,7 +251,8 @@ def run_b200(a):
         for t in list(model.parameters()) + list(model.buffers()) + list(model.arch_parameters()):
             dist.broadcast(t.data, 0)
     use_graph = not a.no_graph and (world == 1 or not a.no_graph_dp)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph)
+    import pcd_flat
+    opt = pcd_flat.FlatAdam(model.parameters(), lr=1e-3)       # torch.optim.Adam's update, one launch over the flat runs
     architect = Architect(model, Namespace(arch_learn_rate=6e-4, arch_wt_decay=1e-3, qst_only=False), reducer=reducer)
     if use_graph:
         architect.optimizer = torch.optim.Adam(model.arch_parameters(), lr=6e-4, betas=(0.5, 0.999), weight_decay=1e-3,

@@ -317,6 +317,25 @@ int pcd_decode_greedy(int T, int B, int H, int E, int V, int start_token, const 
                       const float* w_hh, const float* b_ih, const float* b_hh, const float* h0, const float* c0,
                       const float* w_out, const float* b_out, long long* tokens, float* work, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer-side elementwise operations over a short table of flat runs.  The search step updates all 732 parameter
+ * tensors several times per step outside the network — w' = w - eta * dL/dw (darts_vqa/pcdarts/architect_vqa.py:35-38),
+ * w +- R v of the finite-difference Hessian-vector product (:106-118), clip_grad_norm_ and Adam
+ * (darts_vqa/experiment.py:196-198).  The search network's parameters sit back to back in one arena and their gradients
+ * come back as one flat buffer per cell, so those tensors are a few dozen contiguous runs: `n` runs (<= pcd_flat_max_runs()),
+ * sizes[i] elements each, one device pointer per run and operand (HOST arrays of device pointers).
+ *   pcd_flat_axpy  : y += (alpha_dev ? alpha * *alpha_dev : alpha) * x
+ *   pcd_flat_scale : y *= *scale_dev
+ *   pcd_flat_sumsq : *out += sum of squares (the caller zeroes *out)
+ *   pcd_flat_adam  : torch.optim.Adam's update (L2-style weight decay); *step_dev = step count AFTER the increment
+ * ---------------------------------------------------------------------------------------------- */
+int pcd_flat_max_runs(void);
+int pcd_flat_axpy(int n, const long long* sizes, float* const* y, float* const* x, const float* alpha_dev, float alpha, void* stream);
+int pcd_flat_scale(int n, const long long* sizes, float* const* y, const float* scale_dev, void* stream);
+int pcd_flat_sumsq(int n, const long long* sizes, float* const* x, double* out, void* stream);
+int pcd_flat_adam(int n, const long long* sizes, float* const* p, float* const* g, float* const* m, float* const* v, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, const float* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 import config
+import pcd_ops
 from pcd_ops import decode_greedy, decode_supported, linear_3xtf32, lstm_forward, vocab_cross_entropy
 from pcdarts.model_search import Network
 
@@ -76,6 +77,8 @@ class QstEncoder(nn.Module):
         h0 = image_embedding.reshape(batch, self.hidden_size)
         if self.deterministic and decode_supported(h0, self.lstm, self.word2vec, self.fc2):
             return decode_greedy(h0, self.lstm, self.word2vec, self.fc2, self.max_length)      # one persistent kernel
+        if self.deterministic:       # greedy decode outside the kernel's envelope: loud unless stock ops were opted in
+            pcd_ops._stock(f"greedy decode with hidden size {self.hidden_size}")
         self.lstm.flatten_parameters()
         h = image_embedding.view(1, -1, self.hidden_size)
         state = (h, h)

@@ -494,7 +494,28 @@ def _gemm_tn(lib, a, lda, b, ldb, c, ldc, m, n, k, bias, split_k, ref):
                                         N.stream_for(ref)), "pcd_gemm_tn_3xtf32")
 
 
-_TC_MIN_FLOP = 5e8      # below this a projection stays on the library SGEMM (measured: the 64-row heads lose ~1 ms/step on the TMA path)
+# Every nn.Linear of the model runs on the tcgen05 GEMM (north_star: "the classifier head ... tensor-core GEMMs"; no library
+# SGEMM behind the back).  PCD_TC_MIN_FLOP=<flops> is an EXPERIMENT knob that sends smaller products to torch's F.linear
+# (measured in round 1: the 64-row heads cost ~1 ms/step more on the TMA path than on cuBLAS); default 0 = never.
+_TC_MIN_FLOP = float(os.environ.get("PCD_TC_MIN_FLOP", "0"))
+
+# Shapes outside the kernels' envelope (a Linear whose depth is not a multiple of 4, an LSTM whose hidden size is not a power
+# of two, ...) raise instead of quietly running stock torch ops.  Tests that pin the reference's toy dimensions (hidden 16,
+# word embedding 10) opt in explicitly with allow_stock_ops(True).
+_ALLOW_STOCK = [False]
+
+
+def allow_stock_ops(on=True):
+    """Opt in to stock torch ops for shapes the native kernels do not take (default: raise).  Returns the previous setting."""
+    prev = _ALLOW_STOCK[0]
+    _ALLOW_STOCK[0] = bool(on)
+    return prev
+
+
+def _stock(what):
+    if not _ALLOW_STOCK[0]:
+        raise RuntimeError(f"{what}: shape not supported by the compiled kernels (PCD_ERR_UNSUPPORTED); "
+                           "pcd_ops.allow_stock_ops(True) opts in to the stock torch op")
 
 
 def _auto_split(m, n, k):
@@ -557,13 +578,16 @@ class Linear3xTF32Function(torch.autograd.Function):
 
 
 def linear_3xtf32(x, weight, bias):
-    """nn.Linear forward on the tensor cores when the shapes allow TMA (rows and depth multiples of 4), else F.linear."""
-    if x.shape[-1] % 4 or not (x.is_cuda or N._emu_lib is not None):
+    """nn.Linear forward on the tensor cores (TMA needs a depth that is a multiple of 4; anything else raises unless
+    allow_stock_ops)."""
+    if not (x.is_cuda or N._emu_lib is not None):
+        raise RuntimeError("pcdarts_sm100 kernels need CUDA tensors (no CPU fallback)")
+    if x.shape[-1] % 4:
+        _stock(f"Linear with in_features = {x.shape[-1]}")
         return torch.nn.functional.linear(x, weight, bias)
     m = x.numel() // x.shape[-1]
-    if x.is_cuda and 2.0 * m * weight.shape[0] * weight.shape[1] < _TC_MIN_FLOP:
-        # tiny products are launch/latency-bound either way; the TMA path adds operand transposes in the backward
-        return torch.nn.functional.linear(x, weight, bias)
+    if _TC_MIN_FLOP > 0 and x.is_cuda and 2.0 * m * weight.shape[0] * weight.shape[1] < _TC_MIN_FLOP:
+        return torch.nn.functional.linear(x, weight, bias)          # experiment knob only (PCD_TC_MIN_FLOP)
     return Linear3xTF32Function.apply(x, weight, bias)
 
 
@@ -629,8 +653,12 @@ class VocabCrossEntropyFunction(torch.autograd.Function):
 
 
 def vocab_cross_entropy(x, weight, bias, targets):
-    """Fused projection + cross-entropy (ignore target < 0, mean over the rest); plain torch when TMA cannot take the shape."""
-    if x.shape[-1] % 4 or not (x.is_cuda or N._emu_lib is not None):
+    """Fused projection + cross-entropy (ignore target < 0, mean over the rest); a depth that is not a multiple of 4 raises
+    unless allow_stock_ops."""
+    if not (x.is_cuda or N._emu_lib is not None):
+        raise RuntimeError("pcdarts_sm100 kernels need CUDA tensors (no CPU fallback)")
+    if x.shape[-1] % 4:
+        _stock(f"vocabulary projection with depth {x.shape[-1]}")
         logits = torch.nn.functional.linear(x, weight, bias)
         return torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), targets.reshape(-1), ignore_index=-100)
     return VocabCrossEntropyFunction.apply(x, weight, bias, targets)
@@ -703,35 +731,52 @@ class LstmFunction(torch.autograd.Function):
                 gb if ctx.needs_input_grad[5] else None, gb if ctx.needs_input_grad[6] else None)
 
 
+_LSTM_BATCH = 64        # rows one launch of the cooperative recurrence / decode kernels takes; larger batches are tiled
+
+
 def lstm_supported(x, hidden):
-    """Shapes the cooperative recurrence kernels take: batch <= 64, hidden a power of two in [16, 512], E % 4 == 0."""
-    return (x.is_cuda or N._emu_lib is not None) and x.dim() == 3 and x.shape[1] <= 64 and x.shape[2] % 4 == 0 and \
+    """Shapes the cooperative recurrence kernels take: hidden a power of two in [16, 512], E % 4 == 0 (any batch: tiled by 64)."""
+    return (x.is_cuda or N._emu_lib is not None) and x.dim() == 3 and x.shape[2] % 4 == 0 and \
         16 <= hidden <= 512 and (hidden & (hidden - 1)) == 0
 
 
 def lstm_forward(lstm, x, h0, c0):
-    """nn.LSTM(x, (h0, c0)) for a single-layer unidirectional module, through the native path when the shape allows."""
+    """nn.LSTM(x, (h0, c0)) for a single-layer unidirectional module on the native kernels.  The recurrence is independent per
+    sample, so a batch above 64 runs as ceil(B / 64) launches over contiguous slices (no stock fallback)."""
     if lstm.num_layers != 1 or lstm.bidirectional or lstm.batch_first or not lstm_supported(x, lstm.hidden_size):
+        _stock(f"LSTM(E={x.shape[-1]}, H={lstm.hidden_size}, layers={lstm.num_layers})")
         out, (h, c) = lstm(x, (h0, c0))
         return out, (h, c)
-    out, hT, cT = LstmFunction.apply(x, h0[0], c0[0], lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)
-    return out, (hT.unsqueeze(0), cT.unsqueeze(0))
+    B = x.shape[1]
+    w = (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)
+    if B <= _LSTM_BATCH:
+        out, hT, cT = LstmFunction.apply(x, h0[0], c0[0], *w)
+        return out, (hT.unsqueeze(0), cT.unsqueeze(0))
+    outs, hs, cs = [], [], []
+    for b0 in range(0, B, _LSTM_BATCH):
+        sl = slice(b0, min(B, b0 + _LSTM_BATCH))
+        o, h, c = LstmFunction.apply(x[:, sl].contiguous(), h0[0, sl].contiguous(), c0[0, sl].contiguous(), *w)
+        outs.append(o); hs.append(h); cs.append(c)
+    return torch.cat(outs, 1), (torch.cat(hs, 0).unsqueeze(0), torch.cat(cs, 0).unsqueeze(0))
 
 
 # --------------------------------------------------------------------------------------------
 # Greedy question decode (QstEncoder.generate): one persistent cooperative kernel
 # --------------------------------------------------------------------------------------------
 def decode_supported(h0, lstm, word2vec, proj):
-    """Shapes pcd_decode_greedy takes (single-layer LSTM, batch <= 64, hidden a multiple of 32 up to 512, E % 4 == 0)."""
+    """Shapes pcd_decode_greedy takes (single-layer LSTM, hidden a multiple of 32 up to 512, E % 4 == 0; any batch: tiled by 64)."""
     H = lstm.hidden_size
     return (h0.is_cuda or N._emu_lib is not None) and lstm.num_layers == 1 and not lstm.bidirectional and lstm.bias and \
-        h0.shape[0] <= 64 and 32 <= H <= 512 and H % 32 == 0 and word2vec.embedding_dim % 4 == 0 and \
+        32 <= H <= 512 and H % 32 == 0 and word2vec.embedding_dim % 4 == 0 and \
         proj.in_features == H and proj.bias is not None and h0.dtype == torch.float32
 
 
 def decode_greedy(h0, lstm, word2vec, proj, max_length, start_token=2):
     """tokens (B, max_length) int64 of the greedy decode that starts from `start_token` with h0 = c0 = `h0` (B, H).
     Not differentiable (neither is the reference's argmax): parameters are read detached."""
+    if h0.shape[0] > _LSTM_BATCH:          # independent rows: ceil(B / 64) launches of the persistent kernel
+        return torch.cat([decode_greedy(h0[b0:b0 + _LSTM_BATCH], lstm, word2vec, proj, max_length, start_token)
+                          for b0 in range(0, h0.shape[0], _LSTM_BATCH)], 0)
     lib = N.lib_for(h0)
     B, H = h0.shape
     V, E = word2vec.weight.shape

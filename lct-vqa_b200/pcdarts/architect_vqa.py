@@ -19,6 +19,7 @@ Same arithmetic, different mechanics:
 """
 import torch
 
+import pcd_flat
 import pcd_ops
 
 
@@ -136,7 +137,7 @@ class Architect(object):
         twin = self.unrolled_model()
         with torch.no_grad():
             self._copy_state(twin, model)                                # model_dict carries the live BN buffers
-            torch._foreach_add_(self._lists(twin)[0], grads, alpha=-eta)  # theta - eta * (0 + dtheta)
+            pcd_flat.axpy_([p.data for p in self._lists(twin)[0]], grads, alpha=-eta)   # theta - eta * (0 + dtheta)
         return twin
 
     def _backward_step_unrolled(self, img_train, qst_train, label_train, img_valid, qst_valid, label_valid,
@@ -164,29 +165,24 @@ class Architect(object):
         model = self.model
         params = self._lists(model)[0]
         arch = model.arch_parameters()
+        pdata = [p.data for p in params]
         with torch.no_grad():
-            vnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(vector)))
+            vnorm = pcd_flat.norm(vector)
             if self.device_scalars:
-                R = r / vnorm                                        # 0-dim device tensor
-                step_v = torch._foreach_mul(vector, R)               # R * v once; then +1, -2, +1 of it
-                torch._foreach_add_(params, step_v)
+                R = r / vnorm                                        # 0-dim device tensor: no host synchronisation
+                Rd, Rh = R.reshape(1), 1.0
             else:
                 R = (r / vnorm).item()
-                torch._foreach_add_(params, vector, alpha=R)
+                Rd, Rh = None, R
+            pcd_flat.axpy_(pdata, vector, alpha=Rh, alpha_dev=Rd)        # w + R v, one launch over the flat runs
         with pcd_ops.weight_grads(False):      # only d/d(alpha, beta) is needed at w +- R v
             grads_p = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
         with torch.no_grad():
-            if self.device_scalars:
-                torch._foreach_add_(params, step_v, alpha=-2.0)
-            else:
-                torch._foreach_add_(params, vector, alpha=-2 * R)
+            pcd_flat.axpy_(pdata, vector, alpha=-2.0 * Rh, alpha_dev=Rd)
         with pcd_ops.weight_grads(False):
             grads_n = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
         with torch.no_grad():
-            if self.device_scalars:
-                torch._foreach_add_(params, step_v)
-            else:
-                torch._foreach_add_(params, vector, alpha=R)
+            pcd_flat.axpy_(pdata, vector, alpha=Rh, alpha_dev=Rd)
         self._allreduce(grads_p + grads_n)
         self.last.update(g_pos=grads_p, g_neg=grads_n, R=R, vnorm=vnorm)
         return [(x - y).div_(2 * R) for x, y in zip(grads_p, grads_n)]

@@ -34,7 +34,11 @@ class SearchStep:
             loss.backward()
             if self.reducer is not None:
                 self.reducer([p.grad for p in self._params if p.grad is not None])
-        self.last_grad_norm = nn.utils.clip_grad_norm_(self._params, self.grad_clip)     # the norm BEFORE clipping
+        if hasattr(self.optimizer, "state_tensors"):       # pcd_flat.FlatAdam: norm, clipping and Adam over the flat runs
+            import pcd_flat
+            self.last_grad_norm = pcd_flat.clip_grad_norm_(self._params, self.grad_clip)
+        else:
+            self.last_grad_norm = nn.utils.clip_grad_norm_(self._params, self.grad_clip)     # the norm BEFORE clipping
         self.optimizer.step()
         return loss.detach()
 
@@ -63,6 +67,8 @@ class _TrainingState:
         self.optimizers = list(optimizers)
         self.opt_saved = [{id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
                            for p, st in opt.state.items()} for opt in self.optimizers]
+        self.flat_state = [t for opt in self.optimizers if hasattr(opt, "state_tensors") for t in opt.state_tensors()]
+        self.flat_saved = [t.clone() for t in self.flat_state]
 
     @property
     def tensors(self):
@@ -71,6 +77,8 @@ class _TrainingState:
     def restore(self):
         with torch.no_grad():
             torch._foreach_copy_(self.tensors, self.saved)
+            if self.flat_state:
+                torch._foreach_copy_(self.flat_state, self.flat_saved)
             for opt, saved in zip(self.optimizers, self.opt_saved):
                 for p, st in opt.state.items():
                     old = saved.get(id(p), {})

@@ -665,7 +665,11 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
         arch.optimizer = torch.optim.Adam(m.arch_parameters(), lr=6e-4, betas=(0.5, 0.999), weight_decay=1e-3, capturable=True)
     if unrolled:
         arch.unrolled_model().dropout.p = 0.0
-    opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=graphed)
+    if graphed:           # what bench.py runs: clip + Adam over the flat runs (pcd_flat); the eager arm keeps torch.optim.Adam
+        import pcd_flat
+        opt = pcd_flat.FlatAdam(m.parameters(), lr=1e-3)
+    else:
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
     step = SearchStep(m, arch, opt)
     train = [t.to(device) for t in ref["train"]]
     valid = [t.to(device) for t in ref["valid"]]

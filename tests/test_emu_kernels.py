@@ -202,3 +202,43 @@ def test_graph_warmup_restore_survives_arena_rebinding():
     assert any(not torch.equal(a, b) for a, b in zip(m.parameters(), before))
     snap.restore()
     assert all(torch.equal(a.detach(), b) for a, b in zip(m.parameters(), before))
+
+
+def test_flat_optimizer_ops_match_torch():
+    """pcd_flat: runs found across the parameter arena, axpy / norm / clip / Adam == the torch reference (foreach / per-tensor)."""
+    import pcd_flat
+    torch.manual_seed(0)
+    arena = torch.randn(1000)
+    ps = [arena[0:10].view(2, 5), arena[10:250].view(240), arena[250:1000].view(30, 25), torch.randn(7, 3), torch.randn(5)]
+    garena = torch.randn(240 + 750)
+    gs = [torch.randn(2, 5), garena[0:240], garena[240:990].view(30, 25), torch.randn(7, 3), torch.randn(5)]
+    sizes, ptrs = pcd_flat.co_runs(ps, gs)
+    assert sizes == [10, 990, 21, 5]                      # p contiguous over 0..2, g only over 1..2
+    ref = [p.clone() for p in ps]
+    pcd_flat.axpy_(ps, gs, alpha=-0.25)
+    for a, b, g in zip(ps, ref, gs):
+        assert torch.allclose(a, b - 0.25 * g, rtol=0, atol=1e-6)
+    R = torch.tensor([0.5])
+    pcd_flat.axpy_(ps, gs, alpha=2.0, alpha_dev=R)
+    for a, b, g in zip(ps, ref, gs):
+        assert torch.allclose(a, b + 0.75 * g, rtol=0, atol=1e-6)
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in gs))
+    assert abs(float(pcd_flat.norm(gs)) - float(total)) <= 1e-6 * float(total)
+    # clip + Adam against torch over three steps
+    params = [torch.nn.Parameter(p.clone()) for p in ps]
+    mine = [torch.nn.Parameter(p.clone()) for p in ps]
+    opt_t = torch.optim.Adam(params, lr=1e-2, weight_decay=1e-3)
+    opt_m = pcd_flat.FlatAdam(mine, lr=1e-2, weight_decay=1e-3)
+    for step in range(3):
+        for p, q, g in zip(params, mine, gs):
+            p.grad = (g * (step + 1)).clone()
+            q.grad = (g * (step + 1)).clone()
+        n_t = torch.nn.utils.clip_grad_norm_(params, 5.0)
+        n_m = pcd_flat.clip_grad_norm_(mine, 5.0)
+        assert abs(float(n_t) - float(n_m)) <= 1e-5 * float(n_t)
+        for p, q in zip(params, mine):
+            assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-7)
+        opt_t.step()
+        opt_m.step()
+        for p, q in zip(params, mine):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (step, (p - q).abs().max())
