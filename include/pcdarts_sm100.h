@@ -276,6 +276,14 @@ int pcd_gemm_tn_3xtf32(const float* A, long long lda, const float* B, long long 
                        int M, int N, int K, const float* bias, int split_k, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Small dense products in exact fp32 (FMA): C[i][j] = sum_l A[i*a_i + l*a_l] * B[j*b_j + l*b_l] (+ bias[j]).  The generic strides
+ * express y = x W^T + b, dx = dy W and dW = dy^T x of an nn.Linear without operand transposes.  Used for the answer head
+ * (darts_vqa/vqa_model.py:308-316) and the question encoder's fc2 (:186-190) at batch 64 instead of a library SGEMM.
+ * ---------------------------------------------------------------------------------------------- */
+int pcd_gemm_small_f32(const float* A, long long a_i, long long a_l, const float* B, long long b_j, long long b_l, float* C,
+                       long long ldc, int I, int J, int L, const float* bias, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Cross-entropy over the vocabulary logits, in the padded-pitch layout the projection GEMM writes
  * (darts_vqa/vqa_model.py:356-358: CE(qst_out[:, :-1], qst[:, 1:]); rows with a negative target are ignored).
  *   forward : lse[r] = logsumexp(logits[r, :V]);  loss_rows[r] = lse[r] - logits[r, target[r]]  (0 if ignored)

@@ -1,0 +1,101 @@
+// pcd_gemm_small.cu — FP32-FMA GEMM for the small dense products of the answer head (vqa_model.py:308-316: fc1 512->1000,
+// fc2 1000->1000) and the question encoder's fc2 (:186-190, 1024->512) at batch 64, and their backward products.
+//
+//     C[i][j] = sum_l A(i, l) * B(j, l) (+ bias[j])        A(i, l) = A[i*a_i + l*a_l],  B(j, l) = B[j*b_j + l*b_l]
+//
+// The generic strides express the three products of a Linear layer without operand transposes:
+//     y  = x W^T + b   : A = x  (a_i = K, a_l = 1)   B = W  (b_j = K, b_l = 1)      I = M, J = N, L = K
+//     dx = dy W        : A = dy (a_i = N, a_l = 1)   B = W  (b_j = 1, b_l = K)      I = M, J = K, L = N
+//     dW = dy^T x      : A = dy (a_i = 1, a_l = N)   B = x  (b_j = 1, b_l = K)      I = N, J = K, L = M
+// These products are 0.07 - 0.13 GFLOP with a 2 - 4 MB weight matrix: bound by launch latency and by reading W once, far below
+// the point where the tcgen05 path (pcd_gemm_sm100.cu) pays — and the search network's gradients amplify the 3xTF32 rounding
+// noise of the head ~100x (measured: the weight gradients' median error against float64 goes from 9e-5 to 5e-4 when these
+// run as 3xTF32), so they stay exact fp32.  Round 1 sent them to cuBLAS; this is the library's own kernel instead.
+// 64 x 64 output tile per block, 16-deep chunks through shared memory, 4 x 4 register tile per thread.
+#include "../../include/pcdarts_sm100.h"
+#include "pcd_launch.cuh"
+
+namespace pcd {
+
+struct SmallGemmArgs {
+    const float* A; const float* B; float* C; const float* bias;
+    long long a_i, a_l, b_j, b_l, ldc;
+    int I, J, L;
+};
+
+constexpr int kSgT = 64, kSgK = 16, kSgP = kSgT + 4;
+
+struct KSmallGemm {
+    static constexpr int kMinBlocks = 2;
+    static const char* name() { return "gemm_small_f32"; }
+    static PCD_D void run(const SmallGemmArgs& a, int bx, int by, int, float* sm) {
+        float* As = sm;                       // [kSgK][kSgP]
+        float* Bs = sm + kSgK * kSgP;
+        const int i0 = by * kSgT, j0 = bx * kSgT;
+        PCD_TSTATE(float, acc, [4][4]);
+        PCD_EACH(t) {
+            auto& c = PCD_TREF(acc, t);
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) c[p][q] = 0.f;
+        }
+        for (int l0 = 0; l0 < a.L; l0 += kSgK) {
+            PCD_SYNC();
+            // tile loads: the thread index runs along whichever of (row, depth) is contiguous in memory
+            PCD_FOR(e, kSgT * kSgK) {
+                int r, l;
+                if (a.a_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % kSgT; l = e / kSgT; }
+                const int gi = i0 + r, gl = l0 + l;
+                As[l * kSgP + r] = (gi < a.I && gl < a.L) ? a.A[gi * a.a_i + gl * a.a_l] : 0.f;
+            }
+            PCD_FOR(e, kSgT * kSgK) {
+                int r, l;
+                if (a.b_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % kSgT; l = e / kSgT; }
+                const int gj = j0 + r, gl = l0 + l;
+                Bs[l * kSgP + r] = (gj < a.J && gl < a.L) ? a.B[gj * a.b_j + gl * a.b_l] : 0.f;
+            }
+            PCD_SYNC();
+            PCD_EACH(t) {
+                auto& c = PCD_TREF(acc, t);
+                const int ti = (t >> 4) * 4, tj = (t & 15) * 4;
+#pragma unroll
+                for (int l = 0; l < kSgK; ++l) {
+                    const F4 av = *reinterpret_cast<const F4*>(As + l * kSgP + ti);
+                    const F4 bv = *reinterpret_cast<const F4*>(Bs + l * kSgP + tj);
+                    const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) c[p][q] = fmaf(ar[p], br[q], c[p][q]);
+                }
+            }
+        }
+        PCD_EACH(t) {
+            auto& c = PCD_TREF(acc, t);
+            const int ti = (t >> 4) * 4, tj = (t & 15) * 4;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int gi = i0 + ti + p;
+                if (gi >= a.I) continue;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gj = j0 + tj + q;
+                    if (gj < a.J) a.C[gi * a.ldc + gj] = c[p][q] + (a.bias ? a.bias[gj] : 0.f);
+                }
+            }
+        }
+    }
+};
+
+}  // namespace pcd
+
+using namespace pcd;
+
+extern "C" int pcd_gemm_small_f32(const float* A, long long a_i, long long a_l, const float* B, long long b_j, long long b_l, float* C,
+                                  long long ldc, int I, int J, int L, const float* bias, void* stream) {
+    if (!A || !B || !C || I <= 0 || J <= 0 || L <= 0 || ldc < J) return PCD_ERR_ARG;
+    SmallGemmArgs a;
+    a.A = A; a.B = B; a.C = C; a.bias = bias; a.a_i = a_i; a.a_l = a_l; a.b_j = b_j; a.b_l = b_l; a.ldc = ldc; a.I = I; a.J = J; a.L = L;
+    return launch<KSmallGemm, SmallGemmArgs>(a, (J + kSgT - 1) / kSgT, (I + kSgT - 1) / kSgT, 1, 2 * kSgK * kSgP, stream);
+}

@@ -83,7 +83,7 @@ EXPORTS = ("pcd_launch_count", "pcd_profile_enable", "pcd_profile_num_kernels", 
            "pcd_gemm_tn_3xtf32", "pcd_set_overlap", "pcd_overlap_join", "pcd_ce_forward", "pcd_ce_backward",
            "pcd_transpose_pad", "pcd_lstm_pbuf_floats", "pcd_lstm_forward", "pcd_lstm_backward",
            "pcd_decode_work_floats", "pcd_decode_greedy", "pcd_flat_max_runs", "pcd_flat_axpy", "pcd_flat_scale",
-           "pcd_flat_sumsq", "pcd_flat_adam")
+           "pcd_flat_sumsq", "pcd_flat_adam", "pcd_gemm_small_f32")
 
 
 def _declare(lib):
@@ -122,6 +122,8 @@ def _declare(lib):
     lib.pcd_transpose_pad.argtypes = [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_longlong, vp]
     lib.pcd_gemm_tn_3xtf32.argtypes = [vp, C.c_longlong, vp, C.c_longlong, vp, C.c_longlong, C.c_int, C.c_int, C.c_int, vp,
                                        C.c_int, vp]
+    lib.pcd_gemm_small_f32.argtypes = [vp, C.c_longlong, C.c_longlong, vp, C.c_longlong, C.c_longlong, vp, C.c_longlong,
+                                       C.c_int, C.c_int, C.c_int, vp, vp]
     ll_p, pp = C.POINTER(C.c_longlong), C.POINTER(vp)
     lib.pcd_flat_axpy.argtypes = [C.c_int, ll_p, pp, pp, vp, C.c_float, vp]
     lib.pcd_flat_scale.argtypes = [C.c_int, ll_p, pp, vp, vp]

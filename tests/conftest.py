@@ -18,3 +18,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _stock_ops_off_by_default():
+    """pcd_ops.allow_stock_ops is process-global: cases that opt in (toy dimensions) must not leak into the next test."""
+    yield
+    mod = sys.modules.get("pcd_ops")
+    if mod is not None:
+        mod.allow_stock_ops(False)

@@ -339,7 +339,11 @@ def vqa_batch(seed, device, B=2, H=32):
 
 def make_vqa(device, seed=400):
     import config
+    import pcd_ops
     config.DEVICE = device
+    # the goldens pin the reference at toy dimensions (word embedding 10, hidden 16): outside the LSTM / decode / TMA kernels'
+    # envelope, so these cases opt in to the stock torch ops explicitly (the default is to raise); conftest resets it
+    pcd_ops.allow_stock_ops(True)
     from vqa_model import VqaModel
     m = VqaModel(img_encoder_type="darts", **VQA_DIMS).train()
     _fill(m, seed)
@@ -441,8 +445,10 @@ def lct_batch(seed, device, B=2, H=32):
 def make_lct(device):
     """EF (PC-DARTS VqaModel on the kernels) + W (VGG19 VqaModel, stock torch) + ArchitectLct at the golden case's state."""
     import config
+    import pcd_ops
     config.DEVICE = device
     config.ARCH_TYPE = "darts"
+    pcd_ops.allow_stock_ops(True)          # toy dimensions (hidden 16), see make_vqa
     from models import VqaModel as WModel
     from models_lct import VqaModel as EfModel
     from architect_factory import get_architect
@@ -650,6 +656,8 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
     from pcdarts.architect_vqa import Architect
     from search import GraphedSearchStep, SearchStep
     from vqa_model import VqaModel
+    import pcd_ops
+    pcd_ops.allow_stock_ops(dims is not None)      # full size: every op must be native (a stock fallback raises)
     dims = dict(FULL_DIMS if dims is None else dims)
     dims.pop("qst_vocab_size", None)
     ref = _oracle_search_step(unrolled, B, V, img, dims)

@@ -102,22 +102,59 @@ def test_generate_golden():
     assert P.generate_golden_case("cpu") == 5 * 30 + 9 * 12
 
 
-def test_generate_falls_back_to_the_module_loop_outside_the_kernel_envelope():
-    """Hidden sizes the decode kernel does not take (not a multiple of 32) and sampled (non-deterministic) decoding run the
-    reference's own loop of stock modules; both produce (B, max_length) int64 words in range."""
+def test_generate_outside_the_kernel_envelope_is_loud():
+    """Hidden sizes the decode kernel does not take (not a multiple of 32) RAISE unless stock ops were opted in; sampled
+    (non-deterministic) decoding is the reference's own module loop by design.  Both give (B, max_length) int64 words."""
+    import pcd_ops
     from pcd_ops import decode_supported
     from vqa_model import QstEncoder
     torch.manual_seed(3)
     q = QstEncoder(90, 8, 48, 1, 48, max_length=6)           # H = 48
     img = 0.3 * torch.randn(4, 48)
     assert not decode_supported(img, q.lstm, q.word2vec, q.fc1)
+    with pytest.raises(RuntimeError, match="PCD_ERR_UNSUPPORTED"):
+        q.generate(img)
+    pcd_ops.allow_stock_ops(True)
     words = q.generate(img)
     assert words.shape == (4, 6) and words.dtype == torch.long and int(words.max()) < 90
+    pcd_ops.allow_stock_ops(False)
     q2 = QstEncoder(90, 8, 32, 1, 32, deterministic=False, max_length=5)
     img2 = 0.3 * torch.randn(3, 32)
     assert decode_supported(img2, q2.lstm, q2.word2vec, q2.fc1)      # the shape is fine, the sampling mode is not
     words2 = q2.generate(img2)
     assert words2.shape == (3, 5) and int(words2.min()) >= 0 and int(words2.max()) < 90
+
+
+def test_lstm_outside_the_envelope_raises_and_any_linear_is_native():
+    import pcd_ops
+    y = pcd_ops.linear_3xtf32(torch.ones(3, 10), torch.ones(5, 10), None)        # depth 10: the FMA kernel takes it
+    assert torch.allclose(y, torch.full((3, 5), 10.0))
+    lstm = torch.nn.LSTM(10, 16, 1)
+    with pytest.raises(RuntimeError, match="PCD_ERR_UNSUPPORTED"):
+        pcd_ops.lstm_forward(lstm, torch.randn(4, 2, 10), torch.zeros(1, 2, 16), torch.zeros(1, 2, 16))
+
+
+def test_lstm_and_decode_tile_batches_above_64():
+    """B = 70 runs as two launches over contiguous slices and equals the one-launch result on each slice."""
+    import pcd_ops
+    torch.manual_seed(1)
+    lstm = torch.nn.LSTM(8, 32, 1)
+    x = torch.randn(5, 70, 8, requires_grad=True)
+    h0 = 0.3 * torch.randn(1, 70, 32)
+    out, (h, c) = pcd_ops.lstm_forward(lstm, x, h0, h0)
+    ref, (hr, cr) = lstm(x, (h0, h0))
+    assert torch.allclose(out, ref, atol=2e-5) and torch.allclose(h, hr, atol=2e-5) and torch.allclose(c, cr, atol=2e-5)
+    out.sum().backward()
+    gx = x.grad.clone()
+    x.grad = None
+    ref.sum().backward()
+    assert torch.allclose(gx, x.grad, atol=2e-5)
+    emb = torch.nn.Embedding(50, 8)
+    proj = torch.nn.Linear(32, 50)
+    tok = pcd_ops.decode_greedy(h0[0], lstm, emb, proj, 4)
+    assert tok.shape == (70, 4)
+    assert torch.equal(tok[:64], pcd_ops.decode_greedy(h0[0, :64], lstm, emb, proj, 4))
+    assert torch.equal(tok[64:], pcd_ops.decode_greedy(h0[0, 64:], lstm, emb, proj, 4))
 
 
 def test_make_capturable_moves_adam_step_counters():
@@ -242,3 +279,22 @@ def test_flat_optimizer_ops_match_torch():
         opt_m.step()
         for p, q in zip(params, mine):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (step, (p - q).abs().max())
+
+
+@pytest.mark.parametrize("M,K,N", [(64, 512, 1000), (5, 36, 70), (64, 1024, 512), (3, 16, 12)])
+def test_small_linear_matches_torch(M, K, N):
+    """pcd_gemm_small_f32 (exact-fp32 FMA GEMM of the answer head / question fc2): y, dx, dW, db against F.linear in fp64."""
+    import torch.nn.functional as F
+    from pcd_ops import SmallLinearFunction
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g, requires_grad=True)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).requires_grad_(True)
+    b = torch.randn(N, generator=g, requires_grad=True)
+    G = torch.randn(M, N, generator=g)
+    y = SmallLinearFunction.apply(x, w, b)
+    (y * G).sum().backward()
+    xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yr = F.linear(xr, wr, br)
+    (yr * G.double()).sum().backward()
+    for got, ref, name in ((y, yr, "y"), (x.grad, xr.grad, "dx"), (w.grad, wr.grad, "dw"), (b.grad, br.grad, "db")):
+        P.assert_close(got.double(), ref, 2e-6, name)

@@ -151,6 +151,25 @@ def test_linear_3xtf32_vs_fp64(M, K, N):
         P.assert_close(got.double(), ref, 5e-5, name)
 
 
+@pytest.mark.parametrize("M,K,N", [(64, 512, 1000), (64, 1000, 1000), (64, 1024, 512), (5, 36, 70), (130, 10, 33)])
+def test_small_linear_vs_fp64(M, K, N):
+    """pcd_gemm_small_f32: the answer head / question fc2 products in exact fp32 (no library GEMM), strides instead of transposes."""
+    import torch.nn.functional as F
+    from pcd_ops import SmallLinearFunction
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(DEV).requires_grad_(True)
+    G = torch.randn(M, N, generator=g).to(DEV)
+    y = SmallLinearFunction.apply(x, w, b)
+    (y * G).sum().backward()
+    xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yr = F.linear(xr, wr, br)
+    (yr * G.double()).sum().backward()
+    for got, ref, name in ((y, yr, "y"), (x.grad, xr.grad, "dx"), (w.grad, wr.grad, "dw"), (b.grad, br.grad, "db")):
+        P.assert_close(got.double(), ref, 2e-6, name)
+
+
 # fused vocabulary projection + cross-entropy (ignored rows, padded pitch) vs an fp64 reference
 @pytest.mark.parametrize("B,T,K,V", [(64, 30, 512, 17858), (6, 30, 16, 41), (4, 5, 32, 1000)])
 def test_vocab_cross_entropy_vs_fp64(B, T, K, V):
@@ -173,7 +192,7 @@ def test_vocab_cross_entropy_vs_fp64(B, T, K, V):
 
 
 # persistent-kernel LSTM (tcgen05 projections + cooperative recurrence kernels) vs nn.LSTM in fp64
-@pytest.mark.parametrize("T,B,E,H", [(30, 64, 300, 512), (5, 3, 8, 16), (7, 64, 12, 64)])
+@pytest.mark.parametrize("T,B,E,H", [(30, 64, 300, 512), (5, 3, 8, 16), (7, 64, 12, 64), (30, 256, 300, 512), (6, 130, 12, 64)])
 def test_lstm_vs_fp64(T, B, E, H):
     from pcd_ops import lstm_forward
     g = torch.Generator().manual_seed(T + B + E + H)
@@ -304,7 +323,8 @@ def test_graphed_lct_step_matches_eager():
             assert_close(Lg["gamma_n"][i], Le["gamma_n"][i], 1e-3, f"gamma_n{i}")
 
 
-@pytest.mark.parametrize("B,H,E,V,T", [(64, 512, 300, 17858, 30), (5, 32, 12, 300, 7), (37, 128, 64, 1000, 12), (64, 256, 300, 129, 5)])
+@pytest.mark.parametrize("B,H,E,V,T", [(64, 512, 300, 17858, 30), (5, 32, 12, 300, 7), (37, 128, 64, 1000, 12), (64, 256, 300, 129, 5),
+                                       (130, 512, 300, 17858, 6)])
 def test_greedy_decode(B, H, E, V, T):
     """Persistent greedy-decode kernel vs the reference loop in fp64 (production size first; ragged vocabulary tiles, partial
     batches, fewer gate blocks than vocabulary tiles and the reverse)."""
