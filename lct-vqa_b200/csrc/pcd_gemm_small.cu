@@ -11,7 +11,7 @@
 // the point where the tcgen05 path (pcd_gemm_sm100.cu) pays — and the search network's gradients amplify the 3xTF32 rounding
 // noise of the head ~100x (measured: the weight gradients' median error against float64 goes from 9e-5 to 5e-4 when these
 // run as 3xTF32), so they stay exact fp32.  Round 1 sent them to cuBLAS; this is the library's own kernel instead.
-// 64 x 64 output tile per block, 16-deep chunks through shared memory, 4 x 4 register tile per thread.
+// 64 x 64 (or, for skinny grids, 32 x 32) output tile per block, 16-deep chunks through shared memory, register tiles.
 #include "../../include/pcdarts_sm100.h"
 #include "pcd_launch.cuh"
 
@@ -23,63 +23,66 @@ struct SmallGemmArgs {
     int I, J, L;
 };
 
-constexpr int kSgT = 64, kSgK = 16, kSgP = kSgT + 4;
+constexpr int kSgK = 16;
 
+// T x T output tile per block (T = 64: 4 x 4 register tile per thread; T = 32: 2 x 2, four times as many blocks for the
+// skinny products whose 64 x 64 grid would leave most SMs idle)
+template <int T>
 struct KSmallGemm {
-    static constexpr int kMinBlocks = 2;
-    static const char* name() { return "gemm_small_f32"; }
+    static constexpr int kMinBlocks = 2, MT = T / 16, P = T + 4;
+    static const char* name() { return T == 64 ? "gemm_small_f32_t64" : "gemm_small_f32_t32"; }
     static PCD_D void run(const SmallGemmArgs& a, int bx, int by, int, float* sm) {
-        float* As = sm;                       // [kSgK][kSgP]
-        float* Bs = sm + kSgK * kSgP;
-        const int i0 = by * kSgT, j0 = bx * kSgT;
-        PCD_TSTATE(float, acc, [4][4]);
+        float* As = sm;                       // [kSgK][P]
+        float* Bs = sm + kSgK * P;
+        const int i0 = by * T, j0 = bx * T;
+        PCD_TSTATE(float, acc, [MT][MT]);
         PCD_EACH(t) {
             auto& c = PCD_TREF(acc, t);
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
+            for (int p = 0; p < MT; ++p)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) c[p][q] = 0.f;
+                for (int q = 0; q < MT; ++q) c[p][q] = 0.f;
         }
         for (int l0 = 0; l0 < a.L; l0 += kSgK) {
             PCD_SYNC();
             // tile loads: the thread index runs along whichever of (row, depth) is contiguous in memory
-            PCD_FOR(e, kSgT * kSgK) {
+            PCD_FOR(e, T * kSgK) {
                 int r, l;
-                if (a.a_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % kSgT; l = e / kSgT; }
+                if (a.a_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % T; l = e / T; }
                 const int gi = i0 + r, gl = l0 + l;
-                As[l * kSgP + r] = (gi < a.I && gl < a.L) ? a.A[gi * a.a_i + gl * a.a_l] : 0.f;
+                As[l * P + r] = (gi < a.I && gl < a.L) ? a.A[gi * a.a_i + gl * a.a_l] : 0.f;
             }
-            PCD_FOR(e, kSgT * kSgK) {
+            PCD_FOR(e, T * kSgK) {
                 int r, l;
-                if (a.b_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % kSgT; l = e / kSgT; }
+                if (a.b_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % T; l = e / T; }
                 const int gj = j0 + r, gl = l0 + l;
-                Bs[l * kSgP + r] = (gj < a.J && gl < a.L) ? a.B[gj * a.b_j + gl * a.b_l] : 0.f;
+                Bs[l * P + r] = (gj < a.J && gl < a.L) ? a.B[gj * a.b_j + gl * a.b_l] : 0.f;
             }
             PCD_SYNC();
             PCD_EACH(t) {
                 auto& c = PCD_TREF(acc, t);
-                const int ti = (t >> 4) * 4, tj = (t & 15) * 4;
+                const int ti = (t >> 4) * MT, tj = (t & 15) * MT;
 #pragma unroll
                 for (int l = 0; l < kSgK; ++l) {
-                    const F4 av = *reinterpret_cast<const F4*>(As + l * kSgP + ti);
-                    const F4 bv = *reinterpret_cast<const F4*>(Bs + l * kSgP + tj);
-                    const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+                    float ar[MT], br[MT];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p)
+                    for (int p = 0; p < MT; ++p) { ar[p] = As[l * P + ti + p]; br[p] = Bs[l * P + tj + p]; }
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) c[p][q] = fmaf(ar[p], br[q], c[p][q]);
+                    for (int p = 0; p < MT; ++p)
+#pragma unroll
+                        for (int q = 0; q < MT; ++q) c[p][q] = fmaf(ar[p], br[q], c[p][q]);
                 }
             }
         }
         PCD_EACH(t) {
             auto& c = PCD_TREF(acc, t);
-            const int ti = (t >> 4) * 4, tj = (t & 15) * 4;
+            const int ti = (t >> 4) * MT, tj = (t & 15) * MT;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < MT; ++p) {
                 const int gi = i0 + ti + p;
                 if (gi >= a.I) continue;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < MT; ++q) {
                     const int gj = j0 + tj + q;
                     if (gj < a.J) a.C[gi * a.ldc + gj] = c[p][q] + (a.bias ? a.bias[gj] : 0.f);
                 }
@@ -97,5 +100,7 @@ extern "C" int pcd_gemm_small_f32(const float* A, long long a_i, long long a_l, 
     if (!A || !B || !C || I <= 0 || J <= 0 || L <= 0 || ldc < J) return PCD_ERR_ARG;
     SmallGemmArgs a;
     a.A = A; a.B = B; a.C = C; a.bias = bias; a.a_i = a_i; a.a_l = a_l; a.b_j = b_j; a.b_l = b_l; a.ldc = ldc; a.I = I; a.J = J; a.L = L;
-    return launch<KSmallGemm, SmallGemmArgs>(a, (J + kSgT - 1) / kSgT, (I + kSgT - 1) / kSgT, 1, 2 * kSgK * kSgP, stream);
+    if ((long long)((J + 63) / 64) * ((I + 63) / 64) >= 128)
+        return launch<KSmallGemm<64>, SmallGemmArgs>(a, (J + 63) / 64, (I + 63) / 64, 1, 2 * kSgK * (64 + 4), stream);
+    return launch<KSmallGemm<32>, SmallGemmArgs>(a, (J + 31) / 32, (I + 31) / 32, 1, 2 * kSgK * (32 + 4), stream);
 }

@@ -167,7 +167,9 @@ class Architect(object):
         arch = model.arch_parameters()
         pdata = [p.data for p in params]
         with torch.no_grad():
-            vnorm = pcd_flat.norm(vector)
+            # |v| exactly as before (per-tensor norms, then the norm of those): one multi-tensor launch; R = r / |v| enters
+            # w +- R v, where a different last bit already moves the toy-size goldens (ReLU ties)
+            vnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(vector)))
             if self.device_scalars:
                 R = r / vnorm                                        # 0-dim device tensor: no host synchronisation
                 Rd, Rh = R.reshape(1), 1.0

@@ -689,6 +689,12 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
         step.alpha_step(train, valid, 1e-3, unrolled=unrolled)
         for i, a in enumerate(m.arch_parameters()):           # the alpha-step's own gradient, before the w-step adds to .grad
             assert_close(a.grad, ref["darch"][i], max(REL_TOL, 5.0 * ref["yard"][i]), f"alpha-step darch{i} (fp32 oracle vs its fp64 evaluation: {ref['yard'][i]:.2e})")
+            assert_close(a.detach(), ref["arch_after"][i], 5e-5, f"arch_after{i}")
+        # isolate the w-step: start it from the ORACLE's post-Adam alphas (ours agree to 5e-5, but the network amplifies an alpha
+        # mismatch of 1e-5 into 1e-3 on the weight gradients); the graphed arm cannot be split and widens its tolerance instead
+        with torch.no_grad():
+            for a, v in zip(m.arch_parameters(), ref["arch_after"]):
+                a.copy_(v.to(a.device))
         loss = step.w_step(*train)
     report = {}
     # ---- alpha-step ----
@@ -726,7 +732,8 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
     # norm, which the few tie-flipped tensors (1e-3 .. 1e-2 off) move by ~1e-4
     dnorm = abs(float(step.last_grad_norm) - float(ref["total_norm"])) / float(ref["total_norm"])
     assert dnorm <= 2e-3, f"|grad| before clipping: rel err {dnorm:.3e}"
-    tol_w = REL_TOL + 1.5 * dnorm
+    dalpha_after = max(rel_err(a.detach(), ref["arch_after"][i]) for i, a in enumerate(m.arch_parameters()))
+    tol_w = REL_TOL + 1.5 * dnorm + 100.0 * dalpha_after        # eager arm: dalpha_after == 0 (alphas copied from the oracle)
     coef = min(1.0, 5.0 / (float(step.last_grad_norm) + 1e-6))          # undo the clipping for the fp64 comparison
     e_ours64, e_or64 = [], []
     for k, gr, g32, g64 in zip(ref["keys"], ref["wgrads"], ref["wgrads32"], ref["wgrads64"]):
