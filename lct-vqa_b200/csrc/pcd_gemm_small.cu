@@ -23,40 +23,67 @@ struct SmallGemmArgs {
     int I, J, L;
 };
 
-constexpr int kSgK = 16;
+constexpr int kSgK = 32;
 
 // T x T output tile per block (T = 64: 4 x 4 register tile per thread; T = 32: 2 x 2, four times as many blocks for the
-// skinny products whose 64 x 64 grid would leave most SMs idle)
+// skinny products whose 64 x 64 grid would leave most SMs idle).  The next 32-deep chunk of both operands is fetched into
+// registers while the current one is multiplied out of shared memory: these products are a serial chain of up to 32 chunks,
+// so an exposed global-load latency per chunk (~1 us) was the whole run time of the first version (98 us per launch).
 template <int T>
 struct KSmallGemm {
-    static constexpr int kMinBlocks = 2, MT = T / 16, P = T + 4;
+    static constexpr int kMinBlocks = 2, MT = T / 16, P = T + 4, NL = T * kSgK / kThreads;
     static const char* name() { return T == 64 ? "gemm_small_f32_t64" : "gemm_small_f32_t32"; }
+
+    static PCD_D float fetch(const float* M, long long s_r, long long s_l, int n_r, int L, int r0, int l0, int e) {
+        int r, l;
+        if (s_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % T; l = e / T; }
+        const int gr = r0 + r, gl = l0 + l;
+        return (gr < n_r && gl < L) ? M[gr * s_r + gl * s_l] : 0.f;
+    }
+    static PCD_D void put(float* S, long long s_l, int e, float v) {
+        int r, l;
+        if (s_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % T; l = e / T; }
+        S[l * P + r] = v;
+    }
+
     static PCD_D void run(const SmallGemmArgs& a, int bx, int by, int, float* sm) {
         float* As = sm;                       // [kSgK][P]
         float* Bs = sm + kSgK * P;
         const int i0 = by * T, j0 = bx * T;
         PCD_TSTATE(float, acc, [MT][MT]);
+        PCD_TSTATE(float, pa, [NL]);
+        PCD_TSTATE(float, pb, [NL]);
         PCD_EACH(t) {
             auto& c = PCD_TREF(acc, t);
+            auto& ra = PCD_TREF(pa, t);
+            auto& rb = PCD_TREF(pb, t);
 #pragma unroll
             for (int p = 0; p < MT; ++p)
 #pragma unroll
                 for (int q = 0; q < MT; ++q) c[p][q] = 0.f;
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                ra[k] = fetch(a.A, a.a_i, a.a_l, a.I, a.L, i0, 0, t + k * kThreads);
+                rb[k] = fetch(a.B, a.b_j, a.b_l, a.J, a.L, j0, 0, t + k * kThreads);
+            }
         }
         for (int l0 = 0; l0 < a.L; l0 += kSgK) {
-            PCD_SYNC();
-            // tile loads: the thread index runs along whichever of (row, depth) is contiguous in memory
-            PCD_FOR(e, T * kSgK) {
-                int r, l;
-                if (a.a_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % T; l = e / T; }
-                const int gi = i0 + r, gl = l0 + l;
-                As[l * P + r] = (gi < a.I && gl < a.L) ? a.A[gi * a.a_i + gl * a.a_l] : 0.f;
-            }
-            PCD_FOR(e, T * kSgK) {
-                int r, l;
-                if (a.b_l == 1) { l = e % kSgK; r = e / kSgK; } else { r = e % T; l = e / T; }
-                const int gj = j0 + r, gl = l0 + l;
-                Bs[l * P + r] = (gj < a.J && gl < a.L) ? a.B[gj * a.b_j + gl * a.b_l] : 0.f;
+            PCD_SYNC();                       // the previous chunk's readers are done
+            PCD_EACH(t) {
+                auto& ra = PCD_TREF(pa, t);
+                auto& rb = PCD_TREF(pb, t);
+#pragma unroll
+                for (int k = 0; k < NL; ++k) {
+                    put(As, a.a_l, t + k * kThreads, ra[k]);
+                    put(Bs, a.b_l, t + k * kThreads, rb[k]);
+                }
+                if (l0 + kSgK < a.L) {        // next chunk: in flight while this one is multiplied
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) {
+                        ra[k] = fetch(a.A, a.a_i, a.a_l, a.I, a.L, i0, l0 + kSgK, t + k * kThreads);
+                        rb[k] = fetch(a.B, a.b_j, a.b_l, a.J, a.L, j0, l0 + kSgK, t + k * kThreads);
+                    }
+                }
             }
             PCD_SYNC();
             PCD_EACH(t) {

@@ -42,6 +42,10 @@ class Architect(object):
         self._cache = {}
         # True: keep R = r/||v|| on the device (no host sync) so the whole step can live in a CUDA graph
         self.device_scalars = False
+        # True (CUDA): the two finite-difference passes of the Hessian-vector product, which are independent of each other,
+        # run CONCURRENTLY — w + R v on the model (current stream), w - R v on the persistent twin (side stream)
+        self.concurrent_hvp = False
+        self._side = None
         self.last = {}            # quantities of the last unrolled step, for inspection / tests
 
     # ---- helpers -----------------------------------------------------------------------------------
@@ -137,7 +141,10 @@ class Architect(object):
         twin = self.unrolled_model()
         with torch.no_grad():
             self._copy_state(twin, model)                                # model_dict carries the live BN buffers
-            pcd_flat.axpy_([p.data for p in self._lists(twin)[0]], grads, alpha=-eta)   # theta - eta * (0 + dtheta)
+            if self.device_scalars:       # captured / benchmarked path: one launch over the flat runs
+                pcd_flat.axpy_([p.data for p in self._lists(twin)[0]], grads, alpha=-eta)   # theta - eta * (0 + dtheta)
+            else:                         # eager path: the multi-tensor op the goldens were pinned with (same rounding)
+                torch._foreach_add_(self._lists(twin)[0], grads, alpha=-eta)
         return twin
 
     def _backward_step_unrolled(self, img_train, qst_train, label_train, img_valid, qst_valid, label_valid,
@@ -161,6 +168,42 @@ class Architect(object):
             a.grad = g
         self.last.update(unrolled_loss=unrolled_loss.detach())
 
+    def _hvp_passes_concurrent(self, pdata, vector, Rh, Rd, img, qst, label):
+        """g+ = dL/d(alpha, beta) at w + R v on the model and g- at w - R v on the twin, as two independent branches (two
+        streams; two branches of the CUDA graph when the step is captured).  The reference runs them one after the other on
+        the same module (architect_vqa.py:106-118); the only state the second pass inherits from the first is the BatchNorm
+        running statistics, r2 = 0.9 (0.9 r0 + 0.1 s+) + 0.1 s-, rebuilt below from the two branches' buffers."""
+        model, twin = self.model, self._twin
+        arch = model.arch_parameters()
+        cuda = pdata[0].is_cuda              # (on the CPU emulation build the same code runs without streams: tests)
+        if cuda:
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+        nets = [m for m in model.modules() if hasattr(m, '_arena') and hasattr(m, 'cells')]
+        tnets = [m for m in twin.modules() if hasattr(m, '_arena') and hasattr(m, 'cells')]
+        with torch.no_grad():
+            self._copy_state(twin, model)                        # twin <- (w, BN buffers r0, alphas)
+            r0 = [n._arena().flat('running').clone() for n in nets]
+            tdata = [p.data for p in self._lists(twin)[0]]
+            pcd_flat.axpy_(pdata, vector, alpha=Rh, alpha_dev=Rd)            # model: w + R v
+            pcd_flat.axpy_(tdata, vector, alpha=-Rh, alpha_dev=Rd)           # twin:  w - R v
+        if cuda:
+            self._side.wait_stream(cur)
+        with (torch.cuda.stream(self._side) if cuda else pcd_ops.weight_grads(False)), pcd_ops.weight_grads(False):
+            grads_n = list(torch.autograd.grad(twin._loss(img, qst, label, self.args.qst_only), twin.arch_parameters()))
+        with pcd_ops.weight_grads(False):
+            grads_p = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
+        if cuda:
+            cur.wait_stream(self._side)
+        with torch.no_grad():
+            pcd_flat.axpy_(pdata, vector, alpha=-Rh, alpha_dev=Rd)           # back to w
+            for n, t, r in zip(nets, tnets, r0):                 # BatchNorm buffers as after the two passes in sequence
+                run = n._arena().flat('running')
+                run.mul_(1.0 - pcd_ops.BN_MOMENTUM).add_(t._arena().flat('running')).sub_(r, alpha=1.0 - pcd_ops.BN_MOMENTUM)
+                n._arena().flat('nbt').add_(1)
+        return grads_p, grads_n
+
     def _hessian_vector_product(self, vector, img, qst, label, r=1e-2):
         model = self.model
         params = self._lists(model)[0]
@@ -176,15 +219,27 @@ class Architect(object):
             else:
                 R = (r / vnorm).item()
                 Rd, Rh = None, R
-            pcd_flat.axpy_(pdata, vector, alpha=Rh, alpha_dev=Rd)        # w + R v, one launch over the flat runs
+        if self.concurrent_hvp and self._twin is not None:
+            grads_p, grads_n = self._hvp_passes_concurrent(pdata, vector, Rh, Rd, img, qst, label)
+            self._allreduce(grads_p + grads_n)
+            self.last.update(g_pos=grads_p, g_neg=grads_n, R=R, vnorm=vnorm)
+            return [(x - y).div_(2 * R) for x, y in zip(grads_p, grads_n)]
+
+        def shift(k):       # w += k * R * v: flat kernel on the captured path, the goldens' multi-tensor op on the eager one
+            if self.device_scalars:
+                pcd_flat.axpy_(pdata, vector, alpha=k * Rh, alpha_dev=Rd)
+            else:
+                torch._foreach_add_(params, vector, alpha=k * R)
+        with torch.no_grad():
+            shift(1.0)
         with pcd_ops.weight_grads(False):      # only d/d(alpha, beta) is needed at w +- R v
             grads_p = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
         with torch.no_grad():
-            pcd_flat.axpy_(pdata, vector, alpha=-2.0 * Rh, alpha_dev=Rd)
+            shift(-2.0)
         with pcd_ops.weight_grads(False):
             grads_n = list(torch.autograd.grad(model._loss(img, qst, label, self.args.qst_only), arch))
         with torch.no_grad():
-            pcd_flat.axpy_(pdata, vector, alpha=Rh, alpha_dev=Rd)
+            shift(1.0)
         self._allreduce(grads_p + grads_n)
         self.last.update(g_pos=grads_p, g_neg=grads_n, R=R, vnorm=vnorm)
         return [(x - y).div_(2 * R) for x, y in zip(grads_p, grads_n)]

@@ -73,6 +73,12 @@ def test_architect_emulated(unrolled):
     P.architect_case("cpu", unrolled)
 
 
+def test_architect_concurrent_hvp_emulated():
+    """The two finite-difference passes on two module copies (model at w + R v, twin at w - R v) instead of one after the other on
+    the model: same g+, g-, alpha/beta gradients and BatchNorm side effects as the reference's golden step."""
+    P.architect_case("cpu", True, concurrent_hvp=True)
+
+
 def test_w_step_emulated():
     P.wstep_case("cpu")
 

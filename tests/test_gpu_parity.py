@@ -227,6 +227,11 @@ def test_architect_step_golden(unrolled):
     P.architect_case(DEV, unrolled)
 
 
+def test_architect_step_golden_concurrent_hvp():
+    """Hessian-vector product with its two passes on two streams (model | twin): same golden step."""
+    P.architect_case(DEV, True, concurrent_hvp=True)
+
+
 def test_w_step_golden():
     P.wstep_case(DEV)
 
