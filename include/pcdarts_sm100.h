@@ -13,7 +13,12 @@
  *   - the library never allocates, frees, retains pointers or synchronises; every workspace is
  *     caller-owned; all work is enqueued on `stream` (CUDA-graph capturable).
  *   - return value: 0 on success, a negative pcd_status otherwise; never throws, never exits.
- *   - re-entrant; no global mutable state except idempotent cudaFuncSetAttribute calls.
+ *   - callable from the forward (Python main) thread and the backward (autograd worker) thread of one process: the compute
+ *     entry points keep no state between calls.  Process-global state is limited to: idempotent cudaFuncSetAttribute
+ *     calls; an atomic launch counter (pcd_launch_count); the last CUDA error string (pcd_last_cuda_error, diagnostics
+ *     only); the opt-in weight-gradient overlap (pcd_set_overlap: one library-owned low-priority stream + two events, set
+ *     outside capture, used by one backward at a time); and the opt-in event profiler (pcd_profile_*: a single-threaded
+ *     measurement mode).
  *   - BatchNorm is training-mode only (batch statistics, running stats updated in place,
  *     unbiased variance, num_batches_tracked += 1), eps/momentum as given.
  */
@@ -334,13 +339,15 @@ int pcd_decode_greedy(int T, int B, int H, int E, int V, int start_token, const 
  * sizes[i] elements each, one device pointer per run and operand (HOST arrays of device pointers).
  *   pcd_flat_axpy  : y += (alpha_dev ? alpha * *alpha_dev : alpha) * x
  *   pcd_flat_scale : y *= *scale_dev
- *   pcd_flat_sumsq : *out += sum of squares (the caller zeroes *out)
+ *   pcd_flat_sumsq : *out += sum of squares (the caller zeroes *out); deterministic (fixed reduction order, no atomics: every
+ *                    data-parallel rank must derive the same clip coefficient); work: pcd_flat_sumsq_work(elements) doubles
  *   pcd_flat_adam  : torch.optim.Adam's update (L2-style weight decay); *step_dev = step count AFTER the increment
  * ---------------------------------------------------------------------------------------------- */
 int pcd_flat_max_runs(void);
 int pcd_flat_axpy(int n, const long long* sizes, float* const* y, float* const* x, const float* alpha_dev, float alpha, void* stream);
 int pcd_flat_scale(int n, const long long* sizes, float* const* y, const float* scale_dev, void* stream);
-int pcd_flat_sumsq(int n, const long long* sizes, float* const* x, double* out, void* stream);
+long long pcd_flat_sumsq_work(long long total_elements);
+int pcd_flat_sumsq(int n, const long long* sizes, float* const* x, double* out, double* work, void* stream);
 int pcd_flat_adam(int n, const long long* sizes, float* const* p, float* const* g, float* const* m, float* const* v, float lr,
                   float beta1, float beta2, float eps, float weight_decay, const float* step_dev, void* stream);
 

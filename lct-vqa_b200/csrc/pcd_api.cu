@@ -389,7 +389,7 @@ using namespace pcd;
 extern "C" {
 
 int pcd_version(void) { return PCD_VERSION; }
-long long pcd_launch_count(void) { return g_state.launches; }
+long long pcd_launch_count(void) { return __atomic_load_n(&g_state.launches, __ATOMIC_RELAXED); }
 
 int pcd_profile_enable(int on) {
 #if PCD_CUDA

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restr
 
 static int after_launch(const char* what) {
     LaunchState& L = launch_state();
-    ++L.launches;
+    count_launch(L);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(L.last_err, sizeof L.last_err, "launch %s: %s", what, cudaGetErrorString(e));

@@ -330,7 +330,7 @@ extern "C" int pcd_decode_greedy(int T, int B, int H, int E, int V, int start_to
     a.cand = reinterpret_cast<float2*>(work + (size_t)3 * B * H);
     void* args[] = {&a};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)decode::decode_kernel, dim3(grid), dim3(decode::kT), args, smem, (cudaStream_t)stream);
-    ++L.launches;
+    count_launch(L);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(L.last_err, sizeof L.last_err, "cooperative launch decode: %s", cudaGetErrorString(e));

@@ -82,7 +82,10 @@ struct KScale { static constexpr int kMinBlocks = 4; static const char* name() {
     }
 };
 
-struct SumsqArgs { Table t; double* out; };
+// Sum of squares, DETERMINISTIC (no atomics): under data parallelism every rank derives the clip coefficient from the same
+// averaged gradients, and replicas only stay bit-identical if they all get the same last bit here.  Pass 1: one fp64 partial
+// per 4096-element chunk (fixed tree inside the block); pass 2: one block adds the partials in a fixed order.
+struct SumsqArgs { Table t; double* partials; };
 struct KSumsq { static constexpr int kMinBlocks = 4; static const char* name() { return "flat_sumsq"; }
     static PCD_D void run(const SumsqArgs& a, int x, int, int, float* sm) {
 #if PCD_CUDA
@@ -105,7 +108,7 @@ struct KSumsq { static constexpr int kMinBlocks = 4; static const char* name() {
         if (threadIdx.x == 0) {
             double tot = 0.0;
             for (int w = 0; w < kThreads / 32; ++w) tot += (double)sm[w];
-            atomicAdd(a.out, tot);
+            a.partials[x] = tot;
         }
 #else
         (void)sm;
@@ -113,8 +116,25 @@ struct KSumsq { static constexpr int kMinBlocks = 4; static const char* name() {
         for_chunk(a.t, x, [&](int r, long long off, int cnt) {
             for (int j = 0; j < cnt; ++j) tot += (double)a.t.a[r][off + j] * (double)a.t.a[r][off + j];
         });
-        *a.out += tot;
+        a.partials[x] = tot;
 #endif
+    }
+};
+struct SumFinalArgs { const double* partials; int n; double* out; };
+struct KSumFinal { static constexpr int kMinBlocks = 1; static const char* name() { return "flat_sumsq_final"; }
+    static PCD_D void run(const SumFinalArgs& a, int, int, int, float* sm) {
+        double* part = reinterpret_cast<double*>(sm);        // [kThreads]
+        PCD_FOR(t, kThreads) {
+            double s = 0.0;
+            for (int i = t; i < a.n; i += kThreads) s += a.partials[i];
+            part[t] = s;
+        }
+        PCD_SYNC();
+        PCD_FOR(t, 1) {
+            double s = 0.0;
+            for (int i = 0; i < kThreads; ++i) s += part[i];
+            a.out[0] += s;
+        }
     }
 };
 
@@ -184,13 +204,18 @@ int pcd_flat_scale(int n, const long long* sizes, float* const* y, const float* 
     return launch<KScale, ScaleArgs>(a, chunks(a.t), 1, 1, 0, stream);
 }
 
-/* *out += sum of squares over the runs (the caller zeroes *out) */
-int pcd_flat_sumsq(int n, const long long* sizes, float* const* x, double* out, void* stream) {
-    if (!out) return PCD_ERR_ARG;
+/* *out += sum of squares over the runs (the caller zeroes *out); deterministic; work: pcd_flat_sumsq_work(total elements) doubles */
+long long pcd_flat_sumsq_work(long long total_elements) { return (total_elements + kChunk - 1) / kChunk; }
+int pcd_flat_sumsq(int n, const long long* sizes, float* const* x, double* out, double* work, void* stream) {
+    if (!out || !work) return PCD_ERR_ARG;
     SumsqArgs a;
     PCD_TRY(fill(a.t, n, sizes, x, nullptr, nullptr, nullptr));
-    a.out = out;
-    return launch<KSumsq, SumsqArgs>(a, chunks(a.t), 1, 1, 64, stream);
+    a.partials = work;
+    const int nc = chunks(a.t);
+    PCD_TRY((launch<KSumsq, SumsqArgs>(a, nc, 1, 1, 64, stream)));
+    SumFinalArgs f;
+    f.partials = work; f.n = nc; f.out = out;
+    return launch<KSumFinal, SumFinalArgs>(f, 1, 1, 1, 2 * kThreads, stream);
 }
 
 int pcd_flat_adam(int n, const long long* sizes, float* const* p, float* const* g, float* const* m, float* const* v, float lr, float beta1,

@@ -306,7 +306,7 @@ static int run(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, gz > 0 ? gz : 1);
     gemm_tn_3xtf32_kernel<BN, BK, STAGES, REWRITE_HI><<<grid, kGemmThreads, G::SMEM_BYTES, st>>>(ta, tb, C, ldc, M, N, K, bias, kbps, gz > 1 ? 1 : 0);
     LaunchState& L = launch_state();
-    ++L.launches;
+    count_launch(L);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(L.last_err, sizeof L.last_err, "launch gemm_tn_3xtf32: %s", cudaGetErrorString(e));

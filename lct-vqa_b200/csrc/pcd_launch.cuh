@@ -22,6 +22,9 @@ struct LaunchState {
 #endif
 };
 LaunchState& launch_state();           // defined in pcd_api.cu
+// forward passes launch from the Python main thread, backward passes from autograd's per-device worker thread: the one
+// counter both bump is atomic; the event profiler (pcd_profile_enable) is a single-threaded measurement mode
+inline void count_launch(LaunchState& L) { __atomic_fetch_add(&L.launches, 1LL, __ATOMIC_RELAXED); }
 int register_kernel(const char* name);
 
 #define PCD_TRY(x) do { int rc_ = (x); if (rc_ != PCD_OK) return rc_; } while (0)
@@ -58,7 +61,7 @@ static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, voi
     if (rec >= 0) { L.prof_kid[rec] = kid; cudaEventRecord(L.ev[2 * rec], (cudaStream_t)stream); }
     pcd_kernel<Body, Args><<<dim3(gx, gy, gz), kThreads, bytes, (cudaStream_t)stream>>>(a);
     if (rec >= 0) cudaEventRecord(L.ev[2 * rec + 1], (cudaStream_t)stream);
-    ++L.launches;
+    count_launch(L);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(L.last_err, sizeof L.last_err, "launch %s: %s", Body::name(), cudaGetErrorString(e));
@@ -76,7 +79,7 @@ static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, voi
     if (smem_floats * sizeof(float) > 227 * 1024) return PCD_ERR_UNSUPPORTED;
     static const int kid = register_kernel(Body::name());
     (void)kid;
-    ++L.launches;
+    count_launch(L);
     float* smem = (float*)aligned_alloc(64, (smem_floats * sizeof(float) + 63) / 64 * 64 + 64);
     for (int z = 0; z < gz; ++z)
         for (int y = 0; y < gy; ++y)

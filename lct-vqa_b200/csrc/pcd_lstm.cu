@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kT, 1) lstm_bwd_kernel(BwdArgs a) {
 static int coop_launch(const void* fn, int grid, size_t smem, void** args, cudaStream_t st, const char* what) {
     LaunchState& L = launch_state();
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kT), args, smem, st);
-    ++L.launches;
+    count_launch(L);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(L.last_err, sizeof L.last_err, "cooperative launch %s: %s", what, cudaGetErrorString(e));

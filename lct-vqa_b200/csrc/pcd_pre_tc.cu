@@ -460,7 +460,7 @@ static int map_2d(CUtensorMap* m, const float* p, long long cols, long long rows
 
 static int launched(const char* what) {
     LaunchState& L = launch_state();
-    ++L.launches;
+    count_launch(L);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(L.last_err, sizeof L.last_err, "launch %s: %s", what, cudaGetErrorString(e));

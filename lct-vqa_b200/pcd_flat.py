@@ -69,12 +69,13 @@ def scale_(ys, scale_dev):
 
 
 def norm(xs):
-    """sqrt(sum of squares) over all tensors: 0-dim fp32 device tensor (accumulated in fp64)."""
+    """sqrt(sum of squares) over all tensors: 0-dim fp32 device tensor (accumulated in fp64, fixed order: bit-reproducible)."""
     lib = N.lib_for(xs[0])
     out = torch.zeros((), dtype=torch.float64, device=xs[0].device)
     sizes, ptrs = co_runs(xs)
     for n, sz, (tx,) in _tables(lib, sizes, ptrs):
-        N.check(lib, lib.pcd_flat_sumsq(n, sz, tx, N.ptr(out), N.stream_for(xs[0])), "pcd_flat_sumsq")
+        work = torch.empty(int(lib.pcd_flat_sumsq_work(sum(sz))), dtype=torch.float64, device=xs[0].device)
+        N.check(lib, lib.pcd_flat_sumsq(n, sz, tx, N.ptr(out), N.ptr(work), N.stream_for(xs[0])), "pcd_flat_sumsq")
     return out.sqrt().to(torch.float32)
 
 

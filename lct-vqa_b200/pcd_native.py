@@ -83,7 +83,7 @@ EXPORTS = ("pcd_launch_count", "pcd_profile_enable", "pcd_profile_num_kernels", 
            "pcd_gemm_tn_3xtf32", "pcd_set_overlap", "pcd_overlap_join", "pcd_ce_forward", "pcd_ce_backward",
            "pcd_transpose_pad", "pcd_lstm_pbuf_floats", "pcd_lstm_forward", "pcd_lstm_backward",
            "pcd_decode_work_floats", "pcd_decode_greedy", "pcd_flat_max_runs", "pcd_flat_axpy", "pcd_flat_scale",
-           "pcd_flat_sumsq", "pcd_flat_adam", "pcd_gemm_small_f32")
+           "pcd_flat_sumsq", "pcd_flat_sumsq_work", "pcd_flat_adam", "pcd_gemm_small_f32")
 
 
 def _declare(lib):
@@ -127,7 +127,9 @@ def _declare(lib):
     ll_p, pp = C.POINTER(C.c_longlong), C.POINTER(vp)
     lib.pcd_flat_axpy.argtypes = [C.c_int, ll_p, pp, pp, vp, C.c_float, vp]
     lib.pcd_flat_scale.argtypes = [C.c_int, ll_p, pp, vp, vp]
-    lib.pcd_flat_sumsq.argtypes = [C.c_int, ll_p, pp, vp, vp]
+    lib.pcd_flat_sumsq.argtypes = [C.c_int, ll_p, pp, vp, vp, vp]
+    lib.pcd_flat_sumsq_work.restype = C.c_longlong
+    lib.pcd_flat_sumsq_work.argtypes = [C.c_longlong]
     lib.pcd_flat_adam.argtypes = [C.c_int, ll_p, pp, pp, pp, pp] + [C.c_float] * 5 + [vp, vp]
     return lib
 
