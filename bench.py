@@ -362,6 +362,12 @@ def run_b200(a):
                     "share_of_step": (total_ms / nprof) / (ms / a.steps), "by_kernel": by_kernel}
 
     extras = {}
+    roofline_gemm = None
+    if rank == 0 and not a.no_extras:
+        try:
+            roofline_gemm = gemm_roofline(a, dev)
+        except Exception as e:
+            roofline_gemm = {"error": repr(e)[:200]}
     if not a.no_extras:
         if rank == 0:
             extras["mixedop_fwd_bwd"] = mixedop_microbench(dev, a.batch, hbm)
@@ -389,7 +395,7 @@ def run_b200(a):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": workload(a, world), "e2e": e2e, "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
-               "wgrad_overlap": not a.no_overlap, "concurrent_hvp": bool(a.concurrent_hvp), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
+               "wgrad_overlap": not a.no_overlap, "concurrent_hvp": bool(a.concurrent_hvp), "clocks": clk, "roofline": roofline, "roofline_gemm": roofline_gemm, "cpu_baseline": cpu, "extras": extras,
                "parity": parity,
                "comm": None if reducer is None else reducer.report()}
         emit(out)
@@ -465,6 +471,46 @@ def dp_parity(a, model, reducer, rank, world, dev, shard_batch=8):
             "note": "search-net tensors beyond 1e-4 are ReLU / max-pool tie flips (~1/sqrt(B*H*W), DESIGN.md §2)"}
     dist.barrier()
     return out
+
+
+def gemm_roofline(a, dev):
+    """Second roofline entry (tensor pipe): the vocabulary projection of one pass — M = B*30 rows, K = 512, N = V — through
+    pcd_gemm_tn_3xtf32, algorithmic flops counted ONCE (the 3xTF32 split issues three MMAs per product), against the box's
+    TF32 tensor throughput MEASURED here with a single-pass TF32 GEMM (torch.matmul, allow_tf32, 8192^3, best of 10)."""
+    from pcd_ops import Linear3xTF32Function
+    keep = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        x = torch.randn(8192, 8192, device=dev)
+        y = torch.randn(8192, 8192, device=dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(x, y); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = keep
+    del x, y
+    M, K, Nn = a.batch * 30, DIMS["hidden_size"], a.vocab
+    h = torch.randn(M, K, device=dev)
+    w = torch.randn(Nn, K, device=dev) / K ** 0.5
+    b = torch.zeros(Nn, device=dev)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        Linear3xTF32Function.apply(h, w, b)
+    tot, iters = 0.0, 10
+    for _ in range(iters):
+        flush.zero_()                                   # L2 flush: the 36.6 MB weight matrix must come from HBM as in the step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); Linear3xTF32Function.apply(h, w, b); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / iters
+    achieved = 2.0 * M * Nn * K / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": f"gemm_tn_3xtf32, vocabulary projection forward ({M} x {K} x {Nn})", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "ms": ms, "traffic": None,
+            "peak_source": "measured in this run: torch.matmul fp32 with TF32 tensor cores, 8192^3, best of 10",
+            "note": "algorithmic flops counted once; the kernel issues 3 tcgen05.mma.kind::tf32 per product (hi*hi + hi*lo + lo*hi)"}
 
 
 def lct_alpha_step_bench(a, dev, iters=3):

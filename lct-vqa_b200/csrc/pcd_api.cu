@@ -286,12 +286,14 @@ static int run_pre_forward(int B, int Cin, int Cout, int Hin, int Win, int fr, f
 
 static int run_pre_backward(int B, int Cin, int Cout, int Hin, int Win, int fr, float eps, const float* x, const float* w,
                             const float* y, const float* dy, const double* stats, double* bstats, float* dx, float* gw,
-                            void* stream) {
+                            void* stream, int bstats_done = 0) {
     const int Ho = fr ? Hin / 2 : Hin, Wo = fr ? Win / 2 : Win, HW = Ho * Wo;
-    BnBwdStatArgs s;
-    memset(&s, 0, sizeof s);
-    s.B = B; s.C = Cout; s.HW = HW; s.dy = dy; s.y = y; s.stats = nullptr; s.eps = eps; s.bstats = bstats;
-    PCD_TRY((launch<KBnBwdStats, BnBwdStatArgs>(s, norm_grid_x(B, HW), Cout, 1, bn_bwd_stats_smem_floats(), stream)));
+    if (!bstats_done) {        // (the cell backward accumulates these two sums in the kernel that produces dy: source_grad)
+        BnBwdStatArgs s;
+        memset(&s, 0, sizeof s);
+        s.B = B; s.C = Cout; s.HW = HW; s.dy = dy; s.y = y; s.stats = nullptr; s.eps = eps; s.bstats = bstats;
+        PCD_TRY((launch<KBnBwdStats, BnBwdStatArgs>(s, norm_grid_x(B, HW), Cout, 1, bn_bwd_stats_smem_floats(), stream)));
+    }
     if (!dx && !gw) return PCD_OK;
     PreBwdArgs a;
     memset(&a, 0, sizeof a);
@@ -623,6 +625,7 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
             } else {
                 sg.g0 = nullptr;
                 sg.out = a->work + L.pre_dout[j]; sg.out_ns = (long long)L.C * L.Hs * L.Ws;
+                sg.bn_sums = a->bstats + L.pre_bstats[j];      // sum dy, sum dy * yhat of preprocess j, fused (bstats is zeroed above)
             }
             int m = 0;
             for (int e = 0; e < PCD_MAX_EDGES; ++e) {
@@ -669,11 +672,11 @@ int pcd_cell_backward(const pcd_cell_bwd_args* a, void* stream) {
     PCD_TRY(run_pre_backward(L.B, L.Cpp, L.C, L.H0, L.W0, L.redp, eps, a->s0, a->params + L.pre_par[0],
                              a->saved + L.pre_out[0], a->work + L.pre_dout[0], a->stats + L.pre_stats[0],
                              a->bstats + L.pre_bstats[0], a->need_input_grads ? a->grad_s0 : nullptr,
-                             a->need_param_grads ? a->grad_params + L.pre_par[0] : nullptr, stream));
+                             a->need_param_grads ? a->grad_params + L.pre_par[0] : nullptr, stream, 1));
     PCD_TRY(run_pre_backward(L.B, L.Cp, L.C, L.Hs, L.Ws, 0, eps, a->s1, a->params + L.pre_par[1],
                              a->saved + L.pre_out[1], a->work + L.pre_dout[1], a->stats + L.pre_stats[1],
                              a->bstats + L.pre_bstats[1], a->need_input_grads ? a->grad_s1 : nullptr,
-                             a->need_param_grads ? a->grad_params + L.pre_par[1] : nullptr, stream));
+                             a->need_param_grads ? a->grad_params + L.pre_par[1] : nullptr, stream, 1));
     return PCD_OK;
 }
 

@@ -170,8 +170,27 @@ struct SourceGradArgs {
     long long out_ns;
     int nedges;
     int nimg;              // images per block (blockIdx.z covers ceil(B / nimg)); >1 when planes are small
+    double* bn_sums;       // optional [2][C]: += sum out, sum out * x per channel — the BatchNorm-backward reductions of the
+                           // preprocess op that produced x (x is its normalised output), fused here instead of a separate pass
     SrcEdge e[kMaxSrcEdges];
 };
+
+// block total of two per-thread partial sums -> two fp64 atomics per warp (emulation: the block's tasks ran in one loop)
+PCD_HD void src_bn_flush(double* dst, int C, int ch, float s, float q) {
+#if PCD_CUDA
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(dst + ch, (double)s);
+        atomicAdd(dst + C + ch, (double)q);
+    }
+#else
+    dst[ch] += (double)s;
+    dst[C + ch] += (double)q;
+#endif
+}
 
 // d x[:, ch<c]  = g0 + sum_e [ relu'(x) * (A3 + A5 + D3 + D5 (+ FR)) + max-pool + avg-pool(+identity) partials ]
 // d x[:, q*c+j] = g0 + sum_e beta_e * (dN_e[:, 4j+q]  |  routed through the 2x2 max-pool argmax at stride 2)
@@ -190,6 +209,7 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
         all_merged = all_merged && a.e[k].merged;
         all_s1 = all_s1 && a.e[k].stride == 1;
     }
+    float bs = 0.f, bq = 0.f;          // BatchNorm-backward partial sums (bn_sums): per thread; the emulation loops once per block
     if (ch < c && vec && all_merged) {
         // production path: every load of a task (2 per edge + mask + initial grad) is issued before the first use
         PCD_FOR(tt, nimg * tpp) {
@@ -217,7 +237,10 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
                     v.w += ((pre || xv.w > 0.f) ? m[k].w : 0.f) + q4[k].w;
                 }
             *reinterpret_cast<F4*>(a.out + (long long)n * a.out_ns + (long long)ch * HW + p) = v;
+            bs += (v.x + v.y) + (v.z + v.w);
+            bq = fmaf(v.x, xv.x, fmaf(v.y, xv.y, fmaf(v.z, xv.z, fmaf(v.w, xv.w, bq))));
         }
+        if (a.bn_sums) src_bn_flush(a.bn_sums, a.C, ch, bs, bq);
         return;
     }
     if (ch < c && vec) {
@@ -259,7 +282,10 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
                 v.w += (xv.w > 0.f ? m.w : 0.f) + p4.w + p5.w;
             }
             *reinterpret_cast<F4*>(ob + p) = v;
+            bs += (v.x + v.y) + (v.z + v.w);
+            bq = fmaf(v.x, xv.x, fmaf(v.y, xv.y, fmaf(v.z, xv.z, fmaf(v.w, xv.w, bq))));
         }
+        if (a.bn_sums) src_bn_flush(a.bn_sums, a.C, ch, bs, bq);
         return;
     }
     bool vecb = vec && ch >= c && a.Ws % 4 == 0;
@@ -285,7 +311,13 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
                     v.x = fmaf(beta, d[k].x, v.x); v.y = fmaf(beta, d[k].y, v.y); v.z = fmaf(beta, d[k].z, v.z); v.w = fmaf(beta, d[k].w, v.w);
                 }
             *reinterpret_cast<F4*>(a.out + (long long)n * a.out_ns + (long long)ch * HW + p) = v;
+            if (a.bn_sums) {
+                const F4 xv = *reinterpret_cast<const F4*>(a.x + (long long)n * a.x_ns + (long long)ch * HW + p);
+                bs += (v.x + v.y) + (v.z + v.w);
+                bq = fmaf(v.x, xv.x, fmaf(v.y, xv.y, fmaf(v.z, xv.z, fmaf(v.w, xv.w, bq))));
+            }
         }
+        if (a.bn_sums) src_bn_flush(a.bn_sums, a.C, ch, bs, bq);
         return;
     }
     if (vecb) {
@@ -327,7 +359,13 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
                 }
             }
             *reinterpret_cast<F4*>(ob + p) = v;
+            if (a.bn_sums) {
+                const F4 xv = *reinterpret_cast<const F4*>(xb + p);
+                bs += (v.x + v.y) + (v.z + v.w);
+                bq = fmaf(v.x, xv.x, fmaf(v.y, xv.y, fmaf(v.z, xv.z, fmaf(v.w, xv.w, bq))));
+            }
         }
+        if (a.bn_sums) src_bn_flush(a.bn_sums, a.C, ch, bs, bq);
         return;
     }
     PCD_FOR(tt, nimg * npx) {
@@ -368,7 +406,10 @@ PCD_HD void source_grad_body(const SourceGradArgs& a, int bx, int ch, int nz) {
             }
         }
         ob[p] = v;
+        bs += v;
+        bq = fmaf(v, xb[p], bq);
     }
+    if (a.bn_sums) src_bn_flush(a.bn_sums, a.C, ch, bs, bq);
 }
 
 // ---- arch_grads -----------------------------------------------------------------------------------------
