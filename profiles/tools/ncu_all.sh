@@ -5,7 +5,7 @@ tag=$1
 out=gpurun_out/ncu_$tag
 mkdir -p $out
 python profiles/tools/ncu_wstep.py > $out/plain.log 2>&1 || { echo "plain run failed"; tail -20 $out/plain.log; exit 1; }
-ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'pcd_kernel|gemm_tn|ce_|transpose_pad' --csv --log-file $out/launches.csv python profiles/tools/ncu_wstep.py > $out/launches.log 2>&1
+ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'pcd_kernel|gemm_tn|ce_|transpose_pad|pre_tc|lstm|decode' --csv --log-file $out/launches.csv python profiles/tools/ncu_wstep.py > $out/launches.log 2>&1
 prof() {  # name regex skip
   ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c 1 -f -o $out/$1 python profiles/tools/ncu_wstep.py > $out/$1.log 2>&1
   ncu -i $out/$1.ncu-rep --page raw --csv > $out/$1.raw.csv 2>/dev/null
@@ -42,6 +42,9 @@ for spec in "$@"; do
     v4bwdA4) prof bwdA4_c4_s1 'KBwdA4<\(int\)4, \(int\)1,' 3 ;;
     v4bwdA16) prof bwdA4_c16_s1 'KBwdA4<\(int\)16, \(int\)1,' 3 ;;
     v4bwdA8s2) prof bwdA4_c8_s2 'KBwdA4<\(int\)8, \(int\)2,' 0 ;;
+    pretcdx) prof pre_tc_dx 'pre_tc_dx_kernel' 0 ;;
+    pretcdw) prof pre_tc_dw 'pre_tc_dw_kernel' 0 ;;
+    gemmsmall) prof gemm_small 'KSmallGemm<\(int\)32' 0 ;;
     step) ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $out/step_launches.csv python profiles/tools/ncu_step.py > $out/step_launches.log 2>&1 ;;
   esac
 done
