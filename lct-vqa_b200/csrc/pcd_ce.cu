@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(kCeThreads) ce_bwd_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int cc = c + j;
-        o[j] = (t >= 0 && cc < V) ? sc * (__expf(o[j] - l) - (cc == t ? 1.f : 0.f)) : 0.f;
+        // a row is ignored when its target is negative OR out of range, exactly as ce_fwd scores it (torch raises on >= V)
+        o[j] = (t >= 0 && t < V && cc < V) ? sc * (__expf(o[j] - l) - (cc == t ? 1.f : 0.f)) : 0.f;
     }
     *reinterpret_cast<float4*>(dl + (long long)r * ld + c) = make_float4(o[0], o[1], o[2], o[3]);
 }

@@ -32,10 +32,22 @@ int register_kernel(const char* name);
 #if PCD_CUDA
 #define PCD_D __device__ __forceinline__
 
+// Programmatic dependent launch: a search step is ~1000 short dependent kernels (20 us each), so the drain-then-launch gap
+// between two of them is a measurable share of the step.  Every kernel (1) lets its successor in the stream start launching
+// as soon as all of its own blocks are resident — the successor's blocks then fill the SMs the last wave leaves idle — and
+// (2) waits, before touching memory, until its predecessor has completed and flushed.  Without the launch attribute (or when
+// the predecessor is not a kernel) both instructions are no-ops, so correctness never depends on them.
 template <class Body, class Args>
 __global__ void __launch_bounds__(kThreads, Body::kMinBlocks) pcd_kernel(const Args a) {
     extern __shared__ F4 pcd_smem4[];
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     Body::run(a, blockIdx.x, blockIdx.y, blockIdx.z, reinterpret_cast<float*>(pcd_smem4));
+}
+
+inline bool pdl_enabled() {
+    static const bool on = getenv("PCD_NO_PDL") == nullptr;
+    return on;
 }
 
 template <class Body, class Args>
@@ -59,7 +71,21 @@ static int launch(const Args& a, int gx, int gy, int gz, size_t smem_floats, voi
     static const int kid = register_kernel(Body::name());
     const int rec = (L.prof_on && L.prof_n < kMaxRecords) ? L.prof_n++ : -1;
     if (rec >= 0) { L.prof_kid[rec] = kid; cudaEventRecord(L.ev[2 * rec], (cudaStream_t)stream); }
-    pcd_kernel<Body, Args><<<dim3(gx, gy, gz), kThreads, bytes, (cudaStream_t)stream>>>(a);
+    if (pdl_enabled() && rec < 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx, gy, gz);
+        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.dynamicSmemBytes = bytes;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, pcd_kernel<Body, Args>, a);
+    } else {
+        pcd_kernel<Body, Args><<<dim3(gx, gy, gz), kThreads, bytes, (cudaStream_t)stream>>>(a);
+    }
     if (rec >= 0) cudaEventRecord(L.ev[2 * rec + 1], (cudaStream_t)stream);
     count_launch(L);
     cudaError_t e = cudaGetLastError();

@@ -116,6 +116,18 @@ class Arena:
     def invalidate(self):
         self.valid = False
 
+    def verify(self):
+        """Every parameter / buffer still sits at its place in the arena (the kernels read them by raw pointer: a tensor
+        re-bound by `p.data = ...`, load_state_dict(assign=True) or a parametrization would silently go stale).  ensure() only
+        compares the ends of each group; this full check runs once per optimizer step (SearchStep / Architect)."""
+        self.ensure()
+        for group in (self.params, self.running, self.nbt):
+            if group and not _is_run(group):
+                self.valid = False
+                raise RuntimeError("a parameter or buffer of the search network left its flat arena (re-bound .data?); "
+                                   "call arena.invalidate() + forward, or do not re-bind storages")
+        return self
+
     def flat(self, which):
         """One flat tensor aliasing a whole group ('params' | 'running' | 'nbt') of this arena."""
         group = getattr(self, which)

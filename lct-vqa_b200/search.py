@@ -19,8 +19,15 @@ class SearchStep:
         self.criterion = nn.CrossEntropyLoss()
         self._params = list(model.parameters())
 
+    def _verify_arenas(self):
+        for m in self.model.modules():
+            ar = m.__dict__.get('_pcd_arena')
+            if ar is not None and ar.valid:
+                ar.verify()
+
     def w_step(self, image, question, label):
         """experiment.py:187-200."""
+        self._verify_arenas()
         self.optimizer.zero_grad()
         if self.reducer is not None and hasattr(self.model, "_loss_staged"):
             # data parallel: the backward is cut at the image embedding so that the all-reduce of the question-encoder / head

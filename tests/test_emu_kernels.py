@@ -304,3 +304,21 @@ def test_small_linear_matches_torch(M, K, N):
     (yr * G.double()).sum().backward()
     for got, ref, name in ((y, yr, "y"), (x.grad, xr.grad, "dx"), (w.grad, wr.grad, "dw"), (b.grad, br.grad, "db")):
         P.assert_close(got.double(), ref, 2e-6, name)
+
+
+def test_arena_verify_detects_a_rebound_parameter():
+    """Arena.verify (run once per w-step): a parameter whose .data was re-bound in the MIDDLE of the arena is reported (the
+    cheap per-forward check only looks at the ends of each group)."""
+    from pcdarts.model_search import Cell
+    m = Cell(4, 4, 48, 48, 16, False, False).train()
+    P._fill(m, 3)
+    s0, s1 = torch.randn(1, 48, 8, 8), torch.randn(1, 48, 8, 8)
+    w, w2 = torch.softmax(torch.randn(14, 8), -1), torch.softmax(torch.randn(14), 0)
+    m(s0, s1, w, w2)
+    ar = m._arena()
+    ar.verify()
+    mid = ar.params[len(ar.params) // 2]
+    mid.data = mid.data.clone()
+    ar.ensure()                              # ends unchanged: not noticed here
+    with pytest.raises(RuntimeError, match="left its flat arena"):
+        ar.verify()
