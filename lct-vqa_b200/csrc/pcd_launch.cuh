@@ -32,11 +32,12 @@ int register_kernel(const char* name);
 #if PCD_CUDA
 #define PCD_D __device__ __forceinline__
 
-// Programmatic dependent launch: a search step is ~1000 short dependent kernels (20 us each), so the drain-then-launch gap
-// between two of them is a measurable share of the step.  Every kernel (1) lets its successor in the stream start launching
-// as soon as all of its own blocks are resident — the successor's blocks then fill the SMs the last wave leaves idle — and
-// (2) waits, before touching memory, until its predecessor has completed and flushed.  Without the launch attribute (or when
-// the predecessor is not a kernel) both instructions are no-ops, so correctness never depends on them.
+// Programmatic dependent launch (opt-in, PCD_PDL=1): every kernel (1) lets its successor in the stream start launching as
+// soon as all of its own blocks are resident and (2) waits, before touching memory, until its predecessor has completed and
+// flushed.  Without the launch attribute both instructions are no-ops, so correctness never depends on them.  Measured on
+// the captured search step (B200, round 2, profiles/r02_bench_ab_pdl.json): 38.29 ms with, 36.84 ms without — the early
+// successor blocks hold registers / shared memory of the last wave's SMs while they spin, which costs more than the
+// drain-then-launch gap it hides inside a CUDA graph — so it stays off by default.
 template <class Body, class Args>
 __global__ void __launch_bounds__(kThreads, Body::kMinBlocks) pcd_kernel(const Args a) {
     extern __shared__ F4 pcd_smem4[];
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(kThreads, Body::kMinBlocks) pcd_kernel(const A
 }
 
 inline bool pdl_enabled() {
-    static const bool on = getenv("PCD_NO_PDL") == nullptr;
+    static const bool on = getenv("PCD_PDL") != nullptr && getenv("PCD_PDL")[0] == '1';
     return on;
 }
 

@@ -17,8 +17,10 @@ dev = torch.device('cuda')
 torch.manual_seed(10)
 first_order = len(sys.argv) > 1 and sys.argv[1] == 'first'
 model = VqaModel(qst_vocab_size=17858, img_encoder_type='darts', **bench.DIMS).to(dev).train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+import pcd_flat
+opt = pcd_flat.FlatAdam(model.parameters(), lr=1e-3)          # as bench.py: Adam / clip / axpy over the flat runs
 arch = Architect(model, Namespace(arch_learn_rate=6e-4, arch_wt_decay=1e-3, qst_only=False))
+arch.device_scalars = True
 st = SearchStep(model, arch, opt)
 tr = [t.to(dev) for t in bench.synth_batch(10, 64, 17858, 64)]
 va = [t.to(dev) for t in bench.synth_batch(1010, 64, 17858, 64)]
