@@ -411,7 +411,7 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
-def dp_parity(a, model, reducer, rank, world, dev, shard_batch=8):
+def dp_parity(a, model, reducer, rank, world, dev, shard_batch=None):
     """NCCL parity evidence, after the timed steps, on every rank (it contains collectives):
       1. replica consistency: per-rank fp64 checksums (sum, sum of squares, over every weight and alpha/beta) all-gathered;
          data-parallel replicas must stay BIT-identical;
@@ -419,6 +419,12 @@ def dp_parity(a, model, reducer, rank, world, dev, shard_batch=8):
          the GradReducer over NCCL, compared on rank 0 with the oracle's gradients of the same `world` shards averaged by hand
          (the only place this arm executes oracle/: as the checker)."""
     import torch.distributed as dist
+    # the oracle's cost is bounded by the TOTAL number of samples (16, as 2 x 8 at N = 2), not by the rank count; the other ranks
+    # wait on a gloo barrier (a blocking socket wait): an NCCL barrier spins one host core per rank and, with the oracle's
+    # OpenMP threads oversubscribed, an 8-rank run took > 8 minutes here
+    if shard_batch is None:
+        shard_batch = max(2, 16 // world)
+    cpu_group = dist.new_group(backend="gloo")
     with torch.no_grad():
         tensors = [p.detach() for p in model.parameters()] + [t.detach() for t in model.arch_parameters()]
         cs = torch.stack([torch.stack([t.double().sum() for t in tensors]).sum(),
@@ -442,7 +448,8 @@ def dp_parity(a, model, reducer, rank, world, dev, shard_batch=8):
         model.dropout.p = p_drop
     if rank == 0:
         from oracle import pcdarts_oracle as O
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) - 1))
+        t_oracle = time.time()
         sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
         par, buf = O.split_state(sd)
         keys = [k for k, _ in model.named_parameters()]
@@ -467,9 +474,9 @@ def dp_parity(a, model, reducer, rank, world, dev, shard_batch=8):
         errs.sort(reverse=True)
         out["averaged_grads_vs_oracle"] = {
             "tensors": len(errs), "share_within_1e-4": sum(e <= 1e-4 for e, _ in errs) / len(errs), "worst": errs[:3],
-            "shards": world, "samples_per_shard": shard_batch,
+            "shards": world, "samples_per_shard": shard_batch, "oracle_seconds": round(time.time() - t_oracle, 1),
             "note": "search-net tensors beyond 1e-4 are ReLU / max-pool tie flips (~1/sqrt(B*H*W), DESIGN.md §2)"}
-    dist.barrier()
+    dist.barrier(group=cpu_group)
     return out
 
 

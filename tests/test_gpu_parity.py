@@ -192,7 +192,8 @@ def test_vocab_cross_entropy_vs_fp64(B, T, K, V):
 
 
 # persistent-kernel LSTM (tcgen05 projections + cooperative recurrence kernels) vs nn.LSTM in fp64
-@pytest.mark.parametrize("T,B,E,H", [(30, 64, 300, 512), (5, 3, 8, 16), (7, 64, 12, 64), (30, 256, 300, 512), (6, 130, 12, 64)])
+@pytest.mark.parametrize("T,B,E,H", [(30, 64, 300, 512), (5, 3, 8, 16), (7, 64, 12, 64), (30, 256, 300, 512), (6, 130, 12, 64),
+                                     (5, 20, 12, 128), (4, 33, 8, 256), (3, 17, 8, 32)])
 def test_lstm_vs_fp64(T, B, E, H):
     from pcd_ops import lstm_forward
     g = torch.Generator().manual_seed(T + B + E + H)
