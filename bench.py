@@ -387,7 +387,7 @@ def run_b200(a):
             extras["lct_alpha_step"] = {"error": repr(e)[:200]}
     parity = None
     if world > 1 and not a.no_parity:
-        parity = dp_parity(a, model, reducer, rank, world, dev)
+        parity = dp_parity(a, model, reducer, rank, world, dev, stepper=stepper)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         _, _, cpu = time_cpu(a, 1, 0, budget_s=45.0)
@@ -411,7 +411,7 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
-def dp_parity(a, model, reducer, rank, world, dev, shard_batch=None):
+def dp_parity(a, model, reducer, rank, world, dev, shard_batch=None, stepper=None):
     """NCCL parity evidence, after the timed steps, on every rank (it contains collectives):
       1. replica consistency: per-rank fp64 checksums (sum, sum of squares, over every weight and alpha/beta) all-gathered;
          data-parallel replicas must stay BIT-identical;
@@ -427,12 +427,20 @@ def dp_parity(a, model, reducer, rank, world, dev, shard_batch=None):
     cpu_group = dist.new_group(backend="gloo")
     with torch.no_grad():
         tensors = [p.detach() for p in model.parameters()] + [t.detach() for t in model.arch_parameters()]
+        arch = [t.detach() for t in model.arch_parameters()]
+        gn = getattr(getattr(stepper, "eager", stepper), "last_grad_norm", None) if stepper is not None else None
         cs = torch.stack([torch.stack([t.double().sum() for t in tensors]).sum(),
-                          torch.stack([(t.double() ** 2).sum() for t in tensors]).sum()])
+                          torch.stack([(t.double() ** 2).sum() for t in tensors]).sum(),
+                          torch.stack([t.double().sum() for t in arch]).sum(),
+                          (gn.detach().double().reshape(()) if torch.is_tensor(gn) else torch.zeros((), dtype=torch.float64, device=dev))])
     gathered = [torch.zeros_like(cs) for _ in range(world)]
     dist.all_gather(gathered, cs)
-    out = {"replica_checksums": [[float(x) for x in g.tolist()] for g in gathered],
-           "replicas_identical": all(torch.equal(g, gathered[0]) for g in gathered)}
+    out = {"replica_checksums": [[float(x) for x in g[:2].tolist()] for g in gathered],
+           "replicas_identical": all(torch.equal(g[:3], gathered[0][:3]) for g in gathered),
+           "arch_identical": all(torch.equal(g[2], gathered[0][2]) for g in gathered),
+           # the clip norm of the last w-step: every rank computes it from the same averaged gradients
+           "clip_norm_identical": all(torch.equal(g[3], gathered[0][3]) for g in gathered),
+           "clip_norm": [float(g[3]) for g in gathered]}
     params = list(model.parameters())
     p_drop, model.dropout.p = model.dropout.p, 0.0
     try:

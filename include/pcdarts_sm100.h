@@ -253,6 +253,76 @@ int pcd_preprocess_forward(const pcd_pre_args* a, void* stream);
 int pcd_preprocess_backward(const pcd_pre_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The candidate operations as STAND-ALONE ops on all channels of a tensor — what `OPS[name](C, stride, affine)` modules
+ * run when they are called on their own and what a network derived from a genotype (the reference stops at
+ * Network.genotype(), model_search.py:218-263) is made of.  Training-mode BatchNorm only.  H, W <= 64.
+ *   DilConv  (operations.py:35-47):  dwconv(relu) -> pwconv (+stats) -> bn_apply
+ *   SepConv  (operations.py:50-66):  that unit twice, the first with the stride
+ *   AvgPool2d(3, stride, 1, count_include_pad=False) / MaxPool2d(3, stride, 1)   (operations.py:6-7)
+ * Buffers are the caller's; grad_weight buffers are zeroed by the call and then accumulated.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pcd_dwconv_args {
+    int32_t batch, channels, height, width;      /* input size */
+    int32_t kernel, stride, padding, dilation;   /* kernel 3, 5 or 7; stride 1 or 2 */
+    int32_t relu_input;                          /* 1 => the conv reads relu(x) (and grad_x is masked by x > 0) */
+    const float* x;            /* (B, C, H, W) */
+    const float* weight;       /* (C, 1, k, k) */
+    float* out;                /* fwd: (B, C, Ho, Wo) */
+    const float* grad_out;     /* bwd */
+    float* grad_x;             /* bwd, may be NULL */
+    float* grad_weight;        /* bwd, may be NULL */
+} pcd_dwconv_args;
+int pcd_dwconv_forward(const pcd_dwconv_args* a, void* stream);
+int pcd_dwconv_backward(const pcd_dwconv_args* a, void* stream);
+
+typedef struct pcd_pwconv_args {
+    int32_t batch, c_in, c_out, hw;              /* channels multiples of 4 (<= 128), hw a multiple of 4 */
+    float bn_eps;
+    const float* x;            /* (B, c_in, hw) */
+    const float* weight;       /* (c_out, c_in) */
+    float* z;                  /* fwd: pre-BatchNorm output, written.  bwd: read */
+    double* stats;             /* fwd: sum[c_out], sumsq[c_out], zeroed then accumulated.  bwd: read */
+    const float* grad_y;       /* bwd: gradient w.r.t. the BatchNorm OUTPUT gamma * yhat + beta */
+    const float* gamma;        /* bwd: NULL => 1 */
+    const double* bstats;      /* bwd: sum grad_y [c_out], sum grad_y * yhat [c_out]  (pcd_bn_backward_stats) */
+    float* grad_x;             /* bwd, may be NULL */
+    float* grad_weight;        /* bwd, may be NULL */
+} pcd_pwconv_args;
+int pcd_pwconv_forward(const pcd_pwconv_args* a, void* stream);
+int pcd_pwconv_backward(const pcd_pwconv_args* a, void* stream);
+
+typedef struct pcd_bn_args {
+    int32_t batch, channels, hw;
+    float bn_eps, bn_momentum;
+    const float* z;            /* pre-BatchNorm tensor */
+    const double* stats;       /* sum, sumsq of z per channel (pcd_pwconv_forward) */
+    const float* gamma;        /* NULL => 1 */
+    const float* beta;         /* NULL => 0 */
+    float* running;            /* apply: mean(C), var(C) updated like nn.BatchNorm2d; may be NULL */
+    int64_t* nbt;              /* apply: num_batches_tracked += 1; may be NULL iff running is */
+    float* y;                  /* apply: gamma * (z - mean) * rstd + beta */
+    const float* grad_y;       /* backward_stats */
+    double* bstats;            /* backward_stats: sum grad_y, sum grad_y * yhat (zeroed by the call) = d beta, d gamma */
+} pcd_bn_args;
+int pcd_bn_apply(const pcd_bn_args* a, void* stream);
+int pcd_bn_backward_stats(const pcd_bn_args* a, void* stream);
+
+typedef struct pcd_pool_args {
+    int32_t batch, channels, height, width, stride, is_max;
+    const float* x;
+    float* y;                  /* fwd */
+    const float* grad_y;       /* bwd */
+    float* grad_x;             /* bwd */
+} pcd_pool_args;
+int pcd_pool3x3_forward(const pcd_pool_args* a, void* stream);
+int pcd_pool3x3_backward(const pcd_pool_args* a, void* stream);
+
+/* y[n][c][p] = scale[c] * x[n][c][p] + shift[c]  (NULL => 1 / 0): the affine half of BatchNorm(affine=True) behind the
+ * preprocess kernels' normalised output */
+int pcd_channel_affine(const float* x, const float* scale, const float* shift, float* y, int batch, int channels, int hw,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Network.global_pooling = AdaptiveAvgPool2d(7) followed by flatten
  *                                                darts_vqa/pcdarts/model_search.py:129,176-178
  * ---------------------------------------------------------------------------------------------- */

@@ -8,6 +8,7 @@
 #include "pcd_pre.cuh"
 #include "pcd_edge_v4.cuh"
 #include "pcd_edge_bwd4.cuh"
+#include "pcd_opk.cuh"
 #include "pcd_kernels.h"
 #include "pcd_launch.cuh"
 
@@ -836,6 +837,116 @@ int pcd_adaptive_avgpool_backward(const float* gy, float* gx, int batch, int cha
     const int planes = batch * channels;
     a.ny = planes < 4096 ? planes : 4096;
     return launch<KGapB, GapArgs>(a, (h * w + kThreads - 1) / kThreads, a.ny, 1, 0, stream);
+}
+
+// ---- stand-alone candidate operations (pcd_opk.cuh) ---------------------------------------------------------------------
+static int dw_args(const pcd_dwconv_args* a, DwArgs& d) {
+    memset(&d, 0, sizeof d);
+    d.B = a->batch; d.C = a->channels; d.Hi = a->height; d.Wi = a->width; d.S = a->stride; d.PAD = a->padding; d.DIL = a->dilation;
+    if (d.S < 1 || d.DIL < 1) return PCD_ERR_ARG;
+    d.Ho = (d.Hi + 2 * d.PAD - d.DIL * (a->kernel - 1) - 1) / d.S + 1;
+    d.Wo = (d.Wi + 2 * d.PAD - d.DIL * (a->kernel - 1) - 1) / d.S + 1;
+    d.relu = a->relu_input; d.x = a->x; d.w = a->weight;
+    return PCD_OK;
+}
+
+int pcd_dwconv_forward(const pcd_dwconv_args* a, void* stream) {
+    if (!a || !a->x || !a->weight || !a->out) return PCD_ERR_ARG;
+    DwArgs d;
+    PCD_TRY(dw_args(a, d));
+    d.t = a->out;
+    return launch_dw_fwd(d, a->kernel, stream);
+}
+
+int pcd_dwconv_backward(const pcd_dwconv_args* a, void* stream) {
+    if (!a || !a->x || !a->weight || !a->grad_out) return PCD_ERR_ARG;
+    DwArgs d;
+    PCD_TRY(dw_args(a, d));
+    d.dt = a->grad_out; d.dx = a->grad_x; d.gw = a->grad_weight;
+    if (!d.dx && !d.gw) return PCD_OK;
+    if (d.gw) PCD_TRY(zero_async(d.gw, (size_t)a->channels * a->kernel * a->kernel * sizeof(float), stream));
+    return launch_dw_bwd(d, a->kernel, stream);
+}
+
+static void pw_args(const pcd_pwconv_args* a, PwArgs& p) {
+    memset(&p, 0, sizeof p);
+    p.B = a->batch; p.Cin = a->c_in; p.Cout = a->c_out; p.HW = a->hw; p.eps = a->bn_eps;
+    p.t = a->x; p.w = a->weight; p.z = a->z; p.stats = a->stats;
+}
+
+int pcd_pwconv_forward(const pcd_pwconv_args* a, void* stream) {
+    if (!a || !a->x || !a->weight || !a->z || !a->stats) return PCD_ERR_ARG;
+    if ((((uintptr_t)a->x) | ((uintptr_t)a->z)) & 15) return PCD_ERR_ALIGN;
+    PwArgs p;
+    pw_args(a, p);
+    PCD_TRY(zero_async(a->stats, (size_t)2 * a->c_out * sizeof(double), stream));
+    return launch_pw_fwd(p, stream);
+}
+
+int pcd_pwconv_backward(const pcd_pwconv_args* a, void* stream) {
+    if (!a || !a->x || !a->weight || !a->z || !a->stats || !a->grad_y || !a->bstats) return PCD_ERR_ARG;
+    if ((((uintptr_t)a->x) | ((uintptr_t)a->z) | ((uintptr_t)a->grad_y) | ((uintptr_t)a->grad_x)) & 15) return PCD_ERR_ALIGN;
+    PwArgs p;
+    pw_args(a, p);
+    p.g = a->grad_y; p.gamma = a->gamma; p.bstats = a->bstats; p.dt = a->grad_x; p.gw = a->grad_weight;
+    if (!p.dt && !p.gw) return PCD_OK;
+    if (p.gw) PCD_TRY(zero_async(p.gw, (size_t)a->c_out * a->c_in * sizeof(float), stream));
+    return launch_pw_bwd(p, stream);
+}
+
+int pcd_bn_apply(const pcd_bn_args* a, void* stream) {
+    if (!a || !a->z || !a->stats || !a->y || (a->running && !a->nbt)) return PCD_ERR_ARG;
+    if (a->batch <= 0 || a->channels <= 0 || a->channels > 65535 || a->hw <= 0) return PCD_ERR_UNSUPPORTED;
+    NormArgs nrm;
+    memset(&nrm, 0, sizeof nrm);
+    nrm.B = a->batch; nrm.C = a->channels; nrm.HW = a->hw; nrm.eps = a->bn_eps; nrm.momentum = a->bn_momentum;
+    nrm.src = a->z; nrm.dst = a->y; nrm.stats = a->stats; nrm.gamma = a->gamma; nrm.bias = a->beta;
+    nrm.running = a->running; nrm.nbt = (long long*)a->nbt;
+    return launch<KNorm, NormArgs>(nrm, norm_grid_x(a->batch, a->hw), a->channels, 1, 0, stream);
+}
+
+int pcd_bn_backward_stats(const pcd_bn_args* a, void* stream) {
+    if (!a || !a->z || !a->stats || !a->grad_y || !a->bstats) return PCD_ERR_ARG;
+    if (a->batch <= 0 || a->channels <= 0 || a->channels > 65535 || a->hw <= 0) return PCD_ERR_UNSUPPORTED;
+    PCD_TRY(zero_async(a->bstats, (size_t)2 * a->channels * sizeof(double), stream));
+    BnBwdStatArgs s;
+    memset(&s, 0, sizeof s);
+    s.B = a->batch; s.C = a->channels; s.HW = a->hw; s.dy = a->grad_y; s.y = a->z; s.stats = a->stats; s.eps = a->bn_eps;
+    s.bstats = a->bstats;
+    return launch<KBnBwdStats, BnBwdStatArgs>(s, norm_grid_x(a->batch, a->hw), a->channels, 1, bn_bwd_stats_smem_floats(), stream);
+}
+
+static int pool_args(const pcd_pool_args* a, PoolArgs& p) {
+    memset(&p, 0, sizeof p);
+    if (a->stride < 1) return PCD_ERR_ARG;
+    p.B = a->batch; p.C = a->channels; p.Hi = a->height; p.Wi = a->width; p.S = a->stride; p.is_max = a->is_max;
+    p.Ho = (p.Hi - 1) / p.S + 1; p.Wo = (p.Wi - 1) / p.S + 1;
+    p.x = a->x;
+    return PCD_OK;
+}
+
+int pcd_pool3x3_forward(const pcd_pool_args* a, void* stream) {
+    if (!a || !a->x || !a->y) return PCD_ERR_ARG;
+    PoolArgs p;
+    PCD_TRY(pool_args(a, p));
+    p.y = a->y;
+    return launch_pool_fwd(p, stream);
+}
+
+int pcd_pool3x3_backward(const pcd_pool_args* a, void* stream) {
+    if (!a || !a->x || !a->grad_y || !a->grad_x) return PCD_ERR_ARG;
+    PoolArgs p;
+    PCD_TRY(pool_args(a, p));
+    p.dy = a->grad_y; p.dx = a->grad_x;
+    return launch_pool_bwd(p, stream);
+}
+
+int pcd_channel_affine(const float* x, const float* scale, const float* shift, float* y, int batch, int channels, int hw, void* stream) {
+    if (!x || !y) return PCD_ERR_ARG;
+    AffineArgs f;
+    memset(&f, 0, sizeof f);
+    f.B = batch; f.C = channels; f.HW = hw; f.x = x; f.scale = scale; f.shift = shift; f.y = y;
+    return launch_affine(f, stream);
 }
 
 }  // extern "C"

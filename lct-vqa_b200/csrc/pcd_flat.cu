@@ -82,14 +82,18 @@ struct KScale { static constexpr int kMinBlocks = 4; static const char* name() {
     }
 };
 
-// Sum of squares, DETERMINISTIC (no atomics): under data parallelism every rank derives the clip coefficient from the same
-// averaged gradients, and replicas only stay bit-identical if they all get the same last bit here.  Pass 1: one fp64 partial
-// per 4096-element chunk (fixed tree inside the block); pass 2: one block adds the partials in a fixed order.
+// Sum of squares, DETERMINISTIC (no atomics) and accumulated in fp64 from the first add: under data parallelism every rank
+// derives the clip coefficient from the same averaged gradients, and replicas only stay bit-identical if they all get the same
+// last bit here.  Pass 1: one fp64 partial per 4096-element chunk (fixed tree inside the block); pass 2: one block adds the
+// partials in a fixed order.  The squares are exact in fp64 and every add rounds at 1e-16, so the fp32 norm does not depend on
+// where the chunk boundaries fall — they move with the number of runs per launch, i.e. with which gradient buffers the
+// allocator happened to place back to back on a rank (fp32 partials made 4 replicas drift apart by ulps:
+// profiles/r02_bench_dp4_drift.json).
 struct SumsqArgs { Table t; double* partials; };
 struct KSumsq { static constexpr int kMinBlocks = 4; static const char* name() { return "flat_sumsq"; }
     static PCD_D void run(const SumsqArgs& a, int x, int, int, float* sm) {
 #if PCD_CUDA
-        float s = 0.f;
+        double s = 0.0;
         const Table& t = a.t;
         const long long total = t.start[t.n], c0 = (long long)x * kChunk;
         for (int k = threadIdx.x; k < kChunk / 4; k += blockDim.x) {
@@ -98,16 +102,17 @@ struct KSumsq { static constexpr int kMinBlocks = 4; static const char* name() {
             int r = find_run(t, i);
             for (int j = 0; j < 4 && i < total; ++j, ++i) {
                 while (i >= t.start[r + 1]) ++r;
-                const float v = t.a[r][i - t.start[r]];
-                s = fmaf(v, v, s);
+                const double v = (double)t.a[r][i - t.start[r]];
+                s = fma(v, v, s);
             }
         }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+        double* smd = reinterpret_cast<double*>(sm);
+        if ((threadIdx.x & 31) == 0) smd[threadIdx.x >> 5] = s;
         __syncthreads();
         if (threadIdx.x == 0) {
             double tot = 0.0;
-            for (int w = 0; w < kThreads / 32; ++w) tot += (double)sm[w];
+            for (int w = 0; w < kThreads / 32; ++w) tot += smd[w];
             a.partials[x] = tot;
         }
 #else

@@ -29,4 +29,16 @@ bool pre_tc_supported(int B, int Cin, int Cout, int H, int W, int fr);
 int launch_pre_tc_fwd(const PreArgs& a, void* stream);
 int launch_pre_tc_bwd(const PreBwdArgs& a, void* stream);
 int launch_pre_bwd(const PreBwdArgs& a, void* stream);
+// stand-alone candidate operations on all channels (pcd_opk.cuh): the derived-architecture network's ops
+struct DwArgs;
+struct PwArgs;
+struct PoolArgs;
+struct AffineArgs;
+int launch_dw_fwd(const DwArgs& a, int KS, void* stream);
+int launch_dw_bwd(const DwArgs& a, int KS, void* stream);
+int launch_pw_fwd(const PwArgs& a, void* stream);
+int launch_pw_bwd(const PwArgs& a, void* stream);
+int launch_pool_fwd(const PoolArgs& a, void* stream);
+int launch_pool_bwd(const PoolArgs& a, void* stream);
+int launch_affine(const AffineArgs& a, void* stream);
 }  // namespace pcd

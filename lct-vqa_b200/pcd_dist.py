@@ -154,4 +154,6 @@ def staged_grads(model, batch, params, reducer, qst_only=False, extra=()):
     reducer.start([g for g in g_enc + g_extra if g is not None])
     reducer.finish()
     by_id = {id(p): g for p, g in zip(rest + enc, g_rest + g_enc)}
+    assert len({g.data_ptr() for g in by_id.values() if g is not None and g.numel()}) == \
+        sum(1 for g in by_id.values() if g is not None and g.numel()), "two parameters share one gradient buffer"
     return loss, [by_id[id(p)] for p in params], g_extra

@@ -75,6 +75,26 @@ class PreArgs(C.Structure):
                     "x", "weight", "running", "nbt", "y", "stats", "grad_y", "grad_x", "grad_weight", "bstats")]
 
 
+class DwConvArgs(C.Structure):
+    _fields_ = [(n, i32) for n in ("batch", "channels", "height", "width", "kernel", "stride", "padding", "dilation",
+                                   "relu_input")] + [(n, vp) for n in ("x", "weight", "out", "grad_out", "grad_x", "grad_weight")]
+
+
+class PwConvArgs(C.Structure):
+    _fields_ = [(n, i32) for n in ("batch", "c_in", "c_out", "hw")] + [("bn_eps", f32)] + \
+        [(n, vp) for n in ("x", "weight", "z", "stats", "grad_y", "gamma", "bstats", "grad_x", "grad_weight")]
+
+
+class BnArgs(C.Structure):
+    _fields_ = [(n, i32) for n in ("batch", "channels", "hw")] + [("bn_eps", f32), ("bn_momentum", f32)] + \
+        [(n, vp) for n in ("z", "stats", "gamma", "beta", "running", "nbt", "y", "grad_y", "bstats")]
+
+
+class PoolArgs(C.Structure):
+    _fields_ = [(n, i32) for n in ("batch", "channels", "height", "width", "stride", "is_max")] + \
+        [(n, vp) for n in ("x", "y", "grad_y", "grad_x")]
+
+
 EXPORTS = ("pcd_launch_count", "pcd_profile_enable", "pcd_profile_num_kernels", "pcd_profile_kernel_name",
            "pcd_profile_collect", "pcd_version", "pcd_strerror", "pcd_is_cuda_build", "pcd_last_cuda_error", "pcd_channel_shuffle",
            "pcd_cell_sizes_of", "pcd_cell_forward", "pcd_cell_backward", "pcd_mixedop_sizes_of",
@@ -83,7 +103,9 @@ EXPORTS = ("pcd_launch_count", "pcd_profile_enable", "pcd_profile_num_kernels", 
            "pcd_gemm_tn_3xtf32", "pcd_set_overlap", "pcd_overlap_join", "pcd_ce_forward", "pcd_ce_backward",
            "pcd_transpose_pad", "pcd_lstm_pbuf_floats", "pcd_lstm_forward", "pcd_lstm_backward",
            "pcd_decode_work_floats", "pcd_decode_greedy", "pcd_flat_max_runs", "pcd_flat_axpy", "pcd_flat_scale",
-           "pcd_flat_sumsq", "pcd_flat_sumsq_work", "pcd_flat_adam", "pcd_gemm_small_f32")
+           "pcd_flat_sumsq", "pcd_flat_sumsq_work", "pcd_flat_adam", "pcd_gemm_small_f32",
+           "pcd_dwconv_forward", "pcd_dwconv_backward", "pcd_pwconv_forward", "pcd_pwconv_backward", "pcd_bn_apply",
+           "pcd_bn_backward_stats", "pcd_pool3x3_forward", "pcd_pool3x3_backward", "pcd_channel_affine")
 
 
 def _declare(lib):
@@ -131,6 +153,11 @@ def _declare(lib):
     lib.pcd_flat_sumsq_work.restype = C.c_longlong
     lib.pcd_flat_sumsq_work.argtypes = [C.c_longlong]
     lib.pcd_flat_adam.argtypes = [C.c_int, ll_p, pp, pp, pp, pp] + [C.c_float] * 5 + [vp, vp]
+    for fn, st in (("pcd_dwconv_forward", DwConvArgs), ("pcd_dwconv_backward", DwConvArgs), ("pcd_pwconv_forward", PwConvArgs),
+                   ("pcd_pwconv_backward", PwConvArgs), ("pcd_bn_apply", BnArgs), ("pcd_bn_backward_stats", BnArgs),
+                   ("pcd_pool3x3_forward", PoolArgs), ("pcd_pool3x3_backward", PoolArgs)):
+        getattr(lib, fn).argtypes = [C.POINTER(st), vp]
+    lib.pcd_channel_affine.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     return lib
 
 

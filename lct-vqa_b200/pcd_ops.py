@@ -778,7 +778,10 @@ class LstmFunction(torch.autograd.Function):
                 gwh = _empty((4 * H, H), torch.float32, dev)
                 _gemm_tn(lib, dgt, mp, ht, mp, gwh, H, 4 * H, H, mp, None, _auto_split(4 * H, H, mp), xc)
         return (gx_in, dh0 if ctx.needs_input_grad[1] else None, dc0 if ctx.needs_input_grad[2] else None, gwi, gwh,
-                gb if ctx.needs_input_grad[5] else None, gb if ctx.needs_input_grad[6] else None)
+                gb if ctx.needs_input_grad[5] else None,
+                # b_ih and b_hh get the same values but must not share one buffer: in-place consumers (the data-parallel
+                # all-reduce, the flat clip scaling) would otherwise touch it twice — concurrently, in the clip kernel
+                (gb.clone() if ctx.needs_input_grad[5] else gb) if ctx.needs_input_grad[6] else None)
 
 
 _LSTM_BATCH = 64        # rows one launch of the cooperative recurrence / decode kernels takes; larger batches are tiled

@@ -163,6 +163,20 @@ def test_lstm_and_decode_tile_batches_above_64():
     assert torch.equal(tok[64:], pcd_ops.decode_greedy(h0[0, 64:], lstm, emb, proj, 4))
 
 
+def test_lstm_bias_grads_do_not_share_a_buffer():
+    """b_ih and b_hh get equal gradients in SEPARATE tensors.  One shared buffer is touched twice by every in-place consumer:
+    under data parallelism the flat clip kernel then scaled it from two thread blocks at once and 4 replicas drifted apart
+    (profiles/r02_bench_dp4_drift.json; scratch/dp_drift.py pinned it to these two parameters)."""
+    import pcd_ops
+    torch.manual_seed(2)
+    lstm = torch.nn.LSTM(8, 32, 1)
+    x = torch.randn(4, 3, 8)
+    h0 = 0.3 * torch.randn(1, 3, 32)
+    out, _ = pcd_ops.lstm_forward(lstm, x, h0, h0)
+    g_ih, g_hh = torch.autograd.grad(out.sum(), [lstm.bias_ih_l0, lstm.bias_hh_l0])
+    assert torch.equal(g_ih, g_hh) and g_ih.data_ptr() != g_hh.data_ptr()
+
+
 def test_make_capturable_moves_adam_step_counters():
     """search.make_capturable flips an optimizer that has already stepped (host-side `step` counters) to the capturable form."""
     from search import make_capturable
