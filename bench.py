@@ -385,6 +385,10 @@ def run_b200(a):
             extras["lct_alpha_step"] = lct_alpha_step_bench(a, dev)
         except Exception as e:      # the headline numbers above do not depend on it
             extras["lct_alpha_step"] = {"error": repr(e)[:200]}
+        try:
+            extras["derived_network_train_pass"] = derived_network_bench(model, dev)
+        except Exception as e:
+            extras["derived_network_train_pass"] = {"error": repr(e)[:200]}
     parity = None
     if world > 1 and not a.no_parity:
         parity = dp_parity(a, model, reducer, rank, world, dev, stepper=stepper)
@@ -602,6 +606,36 @@ def mixedop_microbench(dev, B, hbm):
         res.append({"shape": name, "edges_per_pass": count, "ms": ms, "algorithmic_mb": (fwd + bwd) / 1e6,
                     "gb_per_s": gbs, "frac_of_hbm_peak": gbs / hbm})
     return res
+
+
+def derived_network_bench(model, dev, B=256, img=64):
+    """BASELINE config 5: one training pass (forward + backward + SGD step) of the network DERIVED from the
+    search network's current genotype (pcdarts/model.py, stand-alone op kernels on all channels) at a larger per-GPU batch."""
+    from pcdarts.model import derive
+    net = derive(model.img_encoder.darts).to(dev).train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.025, momentum=0.9, weight_decay=3e-4, foreach=True)
+    x = torch.randn(B, 3, img, img, device=dev)
+    G = torch.randn(B, net.output_ch * 49, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        net(x).backward(G)
+        opt.step()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"genotype_normal": [list(g) for g in net.genotype().normal], "genotype_reduce": [list(g) for g in net.genotype().reduce],
+            "batch": B, "image": img, "ms_per_train_pass": ms, "images_per_s": B / (ms / 1e3),
+            "weights": sum(p.numel() for p in net.parameters()),
+            "note": "first versions of the op kernels (whole planes in shared memory, parity first); eager, no CUDA graph"}
 
 
 def emit(obj):

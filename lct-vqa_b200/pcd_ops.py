@@ -485,13 +485,18 @@ def preprocess_apply(module, x, fr):
         if (k, stride, pad) != (1, 1, 0):
             raise NotImplementedError("only the 1x1/stride 1/pad 0 ReLUConvBN of the search network is accelerated")
         bn = module.op[2]
-    if affine or not module.training:
-        raise NotImplementedError("preprocess kernels implement training-mode BatchNorm with affine=False")
+    if not module.training:
+        raise NotImplementedError("preprocess kernels implement training-mode BatchNorm (batch statistics) only")
     if not hasattr(module, "_pcd_arena"):
         module._pcd_arena = Arena(module)
     ar = module._pcd_arena.ensure()
     meta = (fr, c_in, c_out, (ar.param_ptr, ar.running_ptr, ar.nbt_ptr))
-    return PreprocessFunction.apply(x, meta, *ar.params)
+    convs = [module.conv_1.weight, module.conv_2.weight] if fr else [module.op[1].weight]     # first in the arena, back to back
+    yhat = PreprocessFunction.apply(x, meta, *convs)
+    if affine:          # BatchNorm2d(affine=True): gamma * yhat + beta on the affine kernel (pcd_opmods.ChannelAffineFunction)
+        from pcd_opmods import affine_apply
+        return affine_apply(yhat, bn)
+    return yhat
 
 
 # --------------------------------------------------------------------------------------------

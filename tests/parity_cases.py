@@ -791,3 +791,93 @@ def search_step_vs_oracle(device, unrolled, graphed, B=64, V=17858, img=64, dims
     report.update(worst_wgrad=worst, wgrads_within=within, grad_norm_rel_err=dnorm, wgrad_yardstick=yard_w, oracle32_vs_fp64_darch=ref["yard"],
                   ours_vs_oracle32_darch=[rel_err(a.grad, ref["darch"][i] + ref["warch"][i]) for i, a in enumerate(m.arch_parameters())])
     return report
+
+
+# --------------------------------------------------------------------------------------------
+# stand-alone candidate operations: OPS[name](C, stride, affine) on the native op kernels against the
+# SAME layers in stock torch evaluated in float64 (`stock_forward` = the reference's forward, operations.py:22-104; the
+# CPU suite pins `stock_forward` to the reference's own modules where /root/reference exists)
+# --------------------------------------------------------------------------------------------
+OPS_CASES = [("sep_conv_3x3", 16, 1, True, 2, 16), ("sep_conv_3x3", 32, 2, True, 2, 16), ("sep_conv_5x5", 16, 2, False, 1, 12),
+             ("sep_conv_5x5", 8, 1, True, 2, 10), ("sep_conv_7x7", 8, 1, True, 1, 12), ("dil_conv_3x3", 16, 1, True, 2, 16),
+             ("dil_conv_3x3", 8, 2, True, 1, 12), ("dil_conv_5x5", 32, 2, True, 1, 16), ("dil_conv_5x5", 16, 1, False, 2, 8),
+             ("max_pool_3x3", 8, 1, True, 2, 9), ("max_pool_3x3", 8, 2, True, 2, 12), ("avg_pool_3x3", 4, 1, True, 2, 7),
+             ("avg_pool_3x3", 8, 2, True, 1, 16), ("skip_connect", 32, 2, True, 2, 16), ("skip_connect", 64, 2, False, 1, 8),
+             ("skip_connect", 16, 1, True, 1, 8), ("none", 8, 2, True, 1, 8)]
+
+
+def op_vs_stock(name, C, stride, affine, B, H, device, quantized=False, tol=2e-5):
+    import copy
+    from pcdarts.operations import OPS
+    g = torch.Generator().manual_seed(hash((name, C, stride, H)) % 100003)
+    op = OPS[name](C, stride, affine).train()
+    with torch.no_grad():
+        for p in op.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.4 if p.dim() > 1 else 1.0) + (1.0 if p.dim() == 1 else 0.0))
+    ref = copy.deepcopy(op).double()
+    op = op.to(device)
+    x = torch.randn(B, C, H, H, generator=g)
+    if quantized:       # exact ties in the pool windows, exact zeros at the ReLU
+        x = (x * 2).round() / 2
+    xd = x.to(device).requires_grad_(True)
+    xr = x.double().requires_grad_(True)
+    y = op(xd)
+    yr = ref.stock_forward(xr) if hasattr(ref, "stock_forward") else ref(xr)
+    assert y.shape == yr.shape, (y.shape, yr.shape)
+    gy = torch.randn(yr.shape, generator=g)
+    params = list(op.parameters())
+    got = torch.autograd.grad(y, [xd] + params, gy.to(device), allow_unused=True)
+    exp = torch.autograd.grad(yr, [xr] + list(ref.parameters()), gy.double(), allow_unused=True)
+    assert_close(y.double().cpu(), yr, tol, f"{name} forward")
+    for a_, b_, nm in zip(got, exp, ["dx"] + [n for n, _ in op.named_parameters()]):
+        if b_ is None:
+            assert a_ is None or float(a_.abs().max()) == 0.0, nm
+            continue
+        assert_close(a_.double().cpu(), b_, tol, f"{name} {nm}")
+    for (k, b1), (_, b2) in zip(op.named_buffers(), ref.named_buffers()):
+        if k.endswith("num_batches_tracked"):
+            assert int(b1) == int(b2), k
+        else:
+            assert_close(b1.double().cpu(), b2, 1e-5, f"{name} {k}")
+
+
+TEST_GENOTYPE = dict(
+    normal=[('sep_conv_3x3', 0), ('dil_conv_5x5', 1), ('skip_connect', 0), ('max_pool_3x3', 2), ('avg_pool_3x3', 1),
+            ('sep_conv_5x5', 3), ('dil_conv_3x3', 2), ('skip_connect', 4)],
+    reduce=[('max_pool_3x3', 0), ('sep_conv_5x5', 1), ('skip_connect', 0), ('dil_conv_3x3', 2), ('avg_pool_3x3', 1),
+            ('skip_connect', 2), ('sep_conv_3x3', 3), ('dil_conv_5x5', 0)])
+
+
+def derived_vs_stock(device, B=2, img=32, C=16, layers=4, tol=1e-4, share=0.97):
+    """The network a genotype describes (pcdarts/model.py) on the native op kernels against the same modules as stock torch
+    layers in float64: output, every weight gradient, BatchNorm buffers."""
+    import copy
+    from pcdarts.genotypes import Genotype
+    from pcdarts.model import NetworkDerived
+    torch.manual_seed(11)
+    geno = Genotype(normal=TEST_GENOTYPE["normal"], normal_concat=range(2, 6), reduce=TEST_GENOTYPE["reduce"], reduce_concat=range(2, 6))
+    net = NetworkDerived(C, layers, geno).train()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d) and m.affine:
+                m.weight.copy_(1.0 + 0.2 * torch.randn_like(m.weight))
+                m.bias.copy_(0.2 * torch.randn_like(m.bias))
+    ref = copy.deepcopy(net).double()
+    net = net.to(device)
+    x = torch.randn(B, 3, img, img)
+    y = net(x.to(device))
+    yr = ref(x.double(), stock=True)
+    assert y.shape == yr.shape == (B, net.output_ch * 49)
+    gy = torch.randn(yr.shape)
+    got = torch.autograd.grad(y, list(net.parameters()), gy.to(device))
+    exp = torch.autograd.grad(yr, list(ref.parameters()), gy.double())
+    assert_close(y.double().cpu(), yr, tol, "derived network output")
+    errs = sorted(((rel_err(a_.double().cpu(), b_), n) for a_, b_, (n, _) in zip(got, exp, net.named_parameters())), reverse=True)
+    ok = sum(e <= tol for e, _ in errs) / len(errs)
+    assert ok >= share and errs[0][0] < 50 * tol, (ok, errs[:5])
+    for (k, b1), (_, b2) in zip(net.named_buffers(), ref.named_buffers()):
+        if k.endswith("num_batches_tracked"):
+            assert int(b1) == int(b2), k
+        else:
+            assert_close(b1.double().cpu(), b2, 1e-4, k)
+    return ok, errs[:3]

@@ -378,3 +378,24 @@ def test_search_step_full_size_vs_oracle(unrolled, graphed):
     loss (1e-5), every clipped weight gradient (1e-4; search-network tensors with the tie-flip criterion), BN side effects."""
     rep = P.search_step_vs_oracle(DEV, unrolled, graphed)
     print("full-size search step:", rep)
+
+
+# stand-alone candidate operations on all channels (SURVEY.md §8f-4): native op kernels vs the same layers in float64
+@pytest.mark.parametrize("name,C,stride,affine,B,H", P.OPS_CASES + [
+    ("sep_conv_3x3", 16, 1, True, 8, 64), ("sep_conv_5x5", 32, 2, True, 8, 64), ("dil_conv_5x5", 64, 1, True, 16, 16),
+    ("dil_conv_3x3", 64, 2, True, 8, 32), ("max_pool_3x3", 32, 2, True, 8, 64), ("avg_pool_3x3", 64, 1, True, 16, 16),
+    ("skip_connect", 64, 2, True, 8, 32), ("sep_conv_7x7", 16, 1, True, 4, 32)])
+def test_op_vs_stock(name, C, stride, affine, B, H):
+    P.op_vs_stock(name, C, stride, affine, B, H, DEV)
+
+
+@pytest.mark.parametrize("name,stride", [("max_pool_3x3", 1), ("max_pool_3x3", 2), ("sep_conv_3x3", 1)])
+def test_op_exact_ties(name, stride):
+    P.op_vs_stock(name, 8, stride, True, 2, 12, DEV, quantized=True)
+
+
+@pytest.mark.parametrize("B,img", [(2, 32), (8, 64)])
+def test_derived_network_vs_stock(B, img):
+    """The network a genotype describes (pcdarts/model.py): stem, 4 derived cells, pooling; forward + every weight gradient."""
+    ok, worst = P.derived_vs_stock(DEV, B=B, img=img)
+    print(f"derived network B={B} img={img}: share within 1e-4 = {ok:.3f}, worst {worst}")
