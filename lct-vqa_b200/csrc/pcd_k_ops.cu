@@ -2,6 +2,7 @@
 #include "pcd_opk.cuh"
 #include "pcd_kernels.h"
 #include "pcd_launch.cuh"
+#include <stdlib.h>
 
 namespace pcd {
 
@@ -74,9 +75,16 @@ int launch_pw_fwd(const PwArgs& a, void* stream) {
     return launch<KPwFwd, PwArgs>(a, (a.HW + kPwPx - 1) / kPwPx, a.B, 1, pw_fwd_smem_floats(a.Cin, a.Cout), stream);
 }
 
-int launch_pw_bwd(const PwArgs& a, void* stream) {
-    if (!pw_ok(a)) return PCD_ERR_UNSUPPORTED;
-    return launch<KPwBwd, PwArgs>(a, (a.HW + kPwPx - 1) / kPwPx, a.B, 1, pw_bwd_smem_floats(a.Cin, a.Cout), stream);
+int launch_pw_bwd(const PwArgs& a0, void* stream) {
+    if (!pw_ok(a0)) return PCD_ERR_UNSUPPORTED;
+    PwArgs a = a0;
+    const int nchunks = (a.HW + kPwPx - 1) / kPwPx;
+    // as many chunks per block as still leaves ~4 blocks per SM: fewer global atomics on the (Cout x Cin) weight gradient
+    a.cpb = (int)((long long)a.B * nchunks / 592);
+    if (const char* e = getenv("PCD_PW_CPB")) a.cpb = atoi(e);      // test hook: the multi-chunk walk at small sizes
+    if (a.cpb < 1) a.cpb = 1;
+    if (a.cpb > nchunks) a.cpb = nchunks;
+    return launch<KPwBwd, PwArgs>(a, (nchunks + a.cpb - 1) / a.cpb, a.B, 1, pw_bwd_smem_floats(a.Cin, a.Cout), stream);
 }
 
 static bool pool_ok(const PoolArgs& a) {

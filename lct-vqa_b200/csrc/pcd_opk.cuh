@@ -20,6 +20,7 @@ namespace pcd {
 
 constexpr int kOpMaxHW = 64;       // plane side the whole-plane kernels take
 constexpr int kPwPx = 128;         // pixels per block of the pointwise kernels
+constexpr int kPwPitch = kPwPx + 4; // row pitch of the [channel][pixel] tiles: lanes that walk channels hit different banks
 
 struct DwArgs {
     int B, C, Hi, Wi, Ho, Wo, S, PAD, DIL, relu;
@@ -99,7 +100,15 @@ PCD_HD void dw_bwd_body(const DwArgs& a, int c, int n, float* smem) {
                     for (int kx = 0; kx < KS; ++kx) acc[ky * KS + kx] = fmaf(d, p[ky * a.DIL * PW + kx * a.DIL], acc[ky * KS + kx]);
             }
 #pragma unroll
-            for (int k = 0; k < KS * KS; ++k) pcd_atomic_add(GW + k, acc[k]);
+            for (int k = 0; k < KS * KS; ++k) {
+                float v = acc[k];
+#if PCD_CUDA
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);     // all kThreads lanes are in this loop
+                if ((threadIdx.x & 31) == 0)
+#endif
+                    pcd_atomic_add(GW + k, v);
+            }
         }
     }
     if (a.dx) {
@@ -144,25 +153,26 @@ struct PwArgs {
     const double* bstats;  // bwd: sum g [Cout], sum g*yhat [Cout]
     float* dt;             // bwd, may be null
     float* gw;             // bwd, accumulated (caller zeroes), may be null
+    int cpb;               // bwd: 128-pixel chunks per block (launcher)
 };
 
-PCD_HOSTDEV size_t pw_fwd_smem_floats(int Cin, int Cout) { return (size_t)Cout * Cin + (size_t)Cin * kPwPx + 2 * Cout; }
-PCD_HOSTDEV size_t pw_bwd_smem_floats(int Cin, int Cout) { return (size_t)Cout * Cin + (size_t)(Cin + Cout) * kPwPx + 4 * Cout; }
+PCD_HOSTDEV size_t pw_fwd_smem_floats(int Cin, int Cout) { return (size_t)Cout * Cin + (size_t)Cin * kPwPitch + 2 * Cout; }
+PCD_HOSTDEV size_t pw_bwd_smem_floats(int Cin, int Cout) { return 2 * (size_t)Cout * Cin + (size_t)(Cin + Cout) * kPwPitch + 4 * Cout; }
 
-// tile [C][kPwPx] of a (B, C, HW) tensor, pixels p0 .. p0 + kPwPx - 1 of image n, zero beyond HW
+// tile [C][kPwPitch] of a (B, C, HW) tensor, pixels p0 .. p0 + kPwPx - 1 of image n, zero beyond HW
 PCD_HD void stage_px_tile(float* T, const float* src, int C, int HW, int n, int p0) {
     PCD_FOR(i, C * (kPwPx / 4)) {
         const int ci = i / (kPwPx / 4), p4 = i - ci * (kPwPx / 4), p = p0 + 4 * p4;
         F4 v = {0.f, 0.f, 0.f, 0.f};
         if (p < HW) v = *reinterpret_cast<const F4*>(src + ((long long)n * C + ci) * HW + p);      // HW % 4 == 0
-        *reinterpret_cast<F4*>(T + ci * kPwPx + 4 * p4) = v;
+        *reinterpret_cast<F4*>(T + ci * kPwPitch + 4 * p4) = v;
     }
 }
 
 PCD_HD void pw_fwd_body(const PwArgs& a, int bx, int n, float* smem) {
     float* Ws = smem;                          // [Cout][Cin]
     float* T = Ws + a.Cout * a.Cin;            // [Cin][kPwPx]
-    float* SACC = T + a.Cin * kPwPx;           // [2][Cout]
+    float* SACC = T + a.Cin * kPwPitch;        // [2][Cout]
     const int p0 = bx * kPwPx;
     PCD_FOR(i, a.Cout * a.Cin) Ws[i] = a.w[i];
     PCD_FOR(i, 2 * a.Cout) SACC[i] = 0.f;
@@ -176,7 +186,7 @@ PCD_HD void pw_fwd_body(const PwArgs& a, int bx, int n, float* smem) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
         for (int ci = 0; ci < a.Cin; ++ci) {
-            const F4 tv = *reinterpret_cast<const F4*>(T + ci * kPwPx + 4 * p4);
+            const F4 tv = *reinterpret_cast<const F4*>(T + ci * kPwPitch + 4 * p4);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float w = Ws[(4 * co4 + j) * a.Cin + ci];
@@ -184,14 +194,23 @@ PCD_HD void pw_fwd_body(const PwArgs& a, int bx, int n, float* smem) {
                 acc[j][2] = fmaf(w, tv.z, acc[j][2]); acc[j][3] = fmaf(w, tv.w, acc[j][3]);
             }
         }
-        if (p < a.HW) {
+        const bool live = p < a.HW;          // (tile columns beyond HW hold zeros: they add nothing to the sums)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int co = 4 * co4 + j;
+        for (int j = 0; j < 4; ++j) {
+            const int co = 4 * co4 + j;
+            if (live) {
                 F4 o = {acc[j][0], acc[j][1], acc[j][2], acc[j][3]};
                 *reinterpret_cast<F4*>(a.z + ((long long)n * a.Cout + co) * a.HW + p) = o;
-                const float s = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
-                const float q = fmaf(acc[j][0], acc[j][0], fmaf(acc[j][1], acc[j][1], fmaf(acc[j][2], acc[j][2], acc[j][3] * acc[j][3])));
+            }
+            float s = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+            float q = fmaf(acc[j][0], acc[j][0], fmaf(acc[j][1], acc[j][1], fmaf(acc[j][2], acc[j][2], acc[j][3] * acc[j][3])));
+#if PCD_CUDA
+            // kPwPx / 4 == 32: a warp is one co4 and the 32 pixel strips; the task count is a multiple of 32, so warps are whole
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+            if ((threadIdx.x & 31) == 0)
+#endif
+            {
                 pcd_atomic_add(SACC + co, s);
                 pcd_atomic_add(SACC + a.Cout + co, q);
             }
@@ -203,12 +222,13 @@ PCD_HD void pw_fwd_body(const PwArgs& a, int bx, int n, float* smem) {
 
 PCD_HD void pw_bwd_body(const PwArgs& a, int bx, int n, float* smem) {
     float* Ws = smem;                          // [Cout][Cin]
-    float* T = Ws + a.Cout * a.Cin;            // [Cin][kPwPx]
-    float* DZ = T + a.Cin * kPwPx;             // [Cout][kPwPx]
-    float* K = DZ + a.Cout * kPwPx;            // [4][Cout]: mean, rstd, rstd*gamma*m1', m2
-    const int p0 = bx * kPwPx;
+    float* T = Ws + a.Cout * a.Cin;            // [Cin][kPwPitch]
+    float* DZ = T + a.Cin * kPwPitch;          // [Cout][kPwPitch]
+    float* K = DZ + a.Cout * kPwPitch;         // [4][Cout]: mean, rstd, mean(g), mean(g * yhat)
+    float* GW = K + 4 * a.Cout;                // [Cout][Cin] weight-gradient partial of this block's chunks
     const double cnt = (double)a.B * a.HW;
-    PCD_FOR(i, a.Cout * a.Cin) Ws[i] = a.w[i];
+    const int nchunks = (a.HW + kPwPx - 1) / kPwPx;
+    PCD_FOR(i, a.Cout * a.Cin) { Ws[i] = a.w[i]; GW[i] = 0.f; }
     PCD_FOR(co, a.Cout) {
         BnC b = bn_consts(a.stats, a.Cout, 0, co, cnt, a.eps);
         K[co] = b.mean;
@@ -216,60 +236,70 @@ PCD_HD void pw_bwd_body(const PwArgs& a, int bx, int n, float* smem) {
         K[2 * a.Cout + co] = (float)(a.bstats[co] / cnt);
         K[3 * a.Cout + co] = (float)(a.bstats[a.Cout + co] / cnt);
     }
-    stage_px_tile(T, a.t, a.Cin, a.HW, n, p0);
-    PCD_SYNC();
-    // dz = rstd * gamma * (g - mean(g) - yhat * mean(g * yhat)),  yhat = (z - mean) * rstd
-    PCD_FOR(i, a.Cout * (kPwPx / 4)) {
-        const int co = i / (kPwPx / 4), p4 = i - co * (kPwPx / 4), p = p0 + 4 * p4;
-        F4 o = {0.f, 0.f, 0.f, 0.f};
-        if (p < a.HW) {
-            const long long off = ((long long)n * a.Cout + co) * a.HW + p;
-            const F4 g = *reinterpret_cast<const F4*>(a.g + off), z = *reinterpret_cast<const F4*>(a.z + off);
-            const float mean = K[co], rstd = K[a.Cout + co], m1 = K[2 * a.Cout + co], m2 = K[3 * a.Cout + co];
-            const float k = rstd * (a.gamma ? a.gamma[co] : 1.f);
-            o.x = k * (g.x - m1 - (z.x - mean) * rstd * m2); o.y = k * (g.y - m1 - (z.y - mean) * rstd * m2);
-            o.z = k * (g.z - m1 - (z.z - mean) * rstd * m2); o.w = k * (g.w - m1 - (z.w - mean) * rstd * m2);
-        }
-        *reinterpret_cast<F4*>(DZ + co * kPwPx + 4 * p4) = o;
-    }
-    PCD_SYNC();
-    if (a.dt) {
-        PCD_FOR(task, (a.Cin / 4) * (kPwPx / 4)) {
-            const int ci4 = task / (kPwPx / 4), p4 = task - ci4 * (kPwPx / 4), p = p0 + 4 * p4;
-            float acc[4][4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
-            for (int co = 0; co < a.Cout; ++co) {
-                const F4 d = *reinterpret_cast<const F4*>(DZ + co * kPwPx + 4 * p4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float w = Ws[co * a.Cin + 4 * ci4 + j];
-                    acc[j][0] = fmaf(w, d.x, acc[j][0]); acc[j][1] = fmaf(w, d.y, acc[j][1]);
-                    acc[j][2] = fmaf(w, d.z, acc[j][2]); acc[j][3] = fmaf(w, d.w, acc[j][3]);
-                }
-            }
+    // a block walks `cpb` consecutive 128-pixel chunks of its image: the weight gradient is summed in shared memory across
+    // them (every (co, ci) pair belongs to one thread) and leaves with ONE global atomic per pair and block
+    for (int k = 0; k < a.cpb; ++k) {
+        const int chunk = bx * a.cpb + k;
+        if (chunk >= nchunks) break;
+        const int p0 = chunk * kPwPx;
+        PCD_SYNC();                             // the previous chunk's readers of T / DZ are done
+        stage_px_tile(T, a.t, a.Cin, a.HW, n, p0);
+        PCD_SYNC();
+        // dz = rstd * gamma * (g - mean(g) - yhat * mean(g * yhat)),  yhat = (z - mean) * rstd
+        PCD_FOR(i, a.Cout * (kPwPx / 4)) {
+            const int co = i / (kPwPx / 4), p4 = i - co * (kPwPx / 4), p = p0 + 4 * p4;
+            F4 o = {0.f, 0.f, 0.f, 0.f};
             if (p < a.HW) {
+                const long long off = ((long long)n * a.Cout + co) * a.HW + p;
+                const F4 g = *reinterpret_cast<const F4*>(a.g + off), z = *reinterpret_cast<const F4*>(a.z + off);
+                const float mean = K[co], rstd = K[a.Cout + co], m1 = K[2 * a.Cout + co], m2 = K[3 * a.Cout + co];
+                const float kk = rstd * (a.gamma ? a.gamma[co] : 1.f);
+                o.x = kk * (g.x - m1 - (z.x - mean) * rstd * m2); o.y = kk * (g.y - m1 - (z.y - mean) * rstd * m2);
+                o.z = kk * (g.z - m1 - (z.z - mean) * rstd * m2); o.w = kk * (g.w - m1 - (z.w - mean) * rstd * m2);
+            }
+            *reinterpret_cast<F4*>(DZ + co * kPwPitch + 4 * p4) = o;
+        }
+        PCD_SYNC();
+        if (a.dt) {
+            PCD_FOR(task, (a.Cin / 4) * (kPwPx / 4)) {
+                const int ci4 = task / (kPwPx / 4), p4 = task - ci4 * (kPwPx / 4), p = p0 + 4 * p4;
+                float acc[4][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    F4 o = {acc[j][0], acc[j][1], acc[j][2], acc[j][3]};
-                    *reinterpret_cast<F4*>(a.dt + ((long long)n * a.Cin + 4 * ci4 + j) * a.HW + p) = o;
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+                for (int co = 0; co < a.Cout; ++co) {
+                    const F4 d = *reinterpret_cast<const F4*>(DZ + co * kPwPitch + 4 * p4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float w = Ws[co * a.Cin + 4 * ci4 + j];
+                        acc[j][0] = fmaf(w, d.x, acc[j][0]); acc[j][1] = fmaf(w, d.y, acc[j][1]);
+                        acc[j][2] = fmaf(w, d.z, acc[j][2]); acc[j][3] = fmaf(w, d.w, acc[j][3]);
+                    }
+                }
+                if (p < a.HW) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        F4 o = {acc[j][0], acc[j][1], acc[j][2], acc[j][3]};
+                        *reinterpret_cast<F4*>(a.dt + ((long long)n * a.Cin + 4 * ci4 + j) * a.HW + p) = o;
+                    }
                 }
             }
         }
-    }
-    if (a.gw) {
-        PCD_FOR(task, a.Cout * a.Cin) {
-            const int co = task / a.Cin, ci = task - co * a.Cin;
-            const F4* d = reinterpret_cast<const F4*>(DZ + co * kPwPx);
-            const F4* t = reinterpret_cast<const F4*>(T + ci * kPwPx);
-            float s = 0.f;
-            for (int q = 0; q < kPwPx / 4; ++q)
-                s = fmaf(d[q].x, t[q].x, fmaf(d[q].y, t[q].y, fmaf(d[q].z, t[q].z, fmaf(d[q].w, t[q].w, s))));
-            pcd_atomic_add(a.gw + task, s);
+        if (a.gw) {
+            PCD_FOR(task, a.Cout * a.Cin) {
+                const int co = task / a.Cin, ci = task - co * a.Cin;
+                const F4* d = reinterpret_cast<const F4*>(DZ + co * kPwPitch);
+                const F4* t = reinterpret_cast<const F4*>(T + ci * kPwPitch);
+                float s = 0.f;
+                for (int q = 0; q < kPwPx / 4; ++q)
+                    s = fmaf(d[q].x, t[q].x, fmaf(d[q].y, t[q].y, fmaf(d[q].z, t[q].z, fmaf(d[q].w, t[q].w, s))));
+                GW[task] += s;
+            }
         }
     }
+    PCD_SYNC();
+    if (a.gw) PCD_FOR(task, a.Cout * a.Cin) pcd_atomic_add(a.gw + task, GW[task]);
 }
 
 // ---- 3x3 pools, padding 1 -------------------------------------------------------------------------------------------------

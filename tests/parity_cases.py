@@ -863,21 +863,31 @@ def derived_vs_stock(device, B=2, img=32, C=16, layers=4, tol=1e-4, share=0.97):
                 m.weight.copy_(1.0 + 0.2 * torch.randn_like(m.weight))
                 m.bias.copy_(0.2 * torch.randn_like(m.bias))
     ref = copy.deepcopy(net).double()
+    ref32 = copy.deepcopy(net).to(device)          # the yardstick: the same layers in stock torch fp32
     net = net.to(device)
     x = torch.randn(B, 3, img, img)
     y = net(x.to(device))
     yr = ref(x.double(), stock=True)
+    y32 = ref32(x.to(device), stock=True)
     assert y.shape == yr.shape == (B, net.output_ch * 49)
     gy = torch.randn(yr.shape)
     got = torch.autograd.grad(y, list(net.parameters()), gy.to(device))
     exp = torch.autograd.grad(yr, list(ref.parameters()), gy.double())
+    g32 = torch.autograd.grad(y32, list(ref32.parameters()), gy.to(device))
     assert_close(y.double().cpu(), yr, tol, "derived network output")
     errs = sorted(((rel_err(a_.double().cpu(), b_), n) for a_, b_, (n, _) in zip(got, exp, net.named_parameters())), reverse=True)
+    yard = sorted((rel_err(a_.double().cpu(), b_) for a_, b_ in zip(g32, exp)), reverse=True)
     ok = sum(e <= tol for e, _ in errs) / len(errs)
-    assert ok >= share and errs[0][0] < 50 * tol, (ok, errs[:5])
+    ok32 = sum(e <= tol for e in yard) / len(yard)
+    med, med32 = errs[len(errs) // 2][0], yard[len(yard) // 2]
+    # weight gradients behind batch-statistic BatchNorm and ReLU / max-pool decisions are ill-conditioned at 64 x 64 (stock
+    # torch fp32 itself is 1e-3 .. 1e-2 from float64 there): the bar is the stock fp32 layers' own distance
+    assert ok >= min(share, ok32 - 0.05), (ok, ok32, errs[:5])
+    assert med <= max(1e-5, 2 * med32), (med, med32)
+    assert errs[0][0] <= max(50 * tol, 3 * yard[0]), (errs[:5], yard[:3])
     for (k, b1), (_, b2) in zip(net.named_buffers(), ref.named_buffers()):
         if k.endswith("num_batches_tracked"):
             assert int(b1) == int(b2), k
         else:
             assert_close(b1.double().cpu(), b2, 1e-4, k)
-    return ok, errs[:3]
+    return ok, (errs[:3], {"stock_fp32_share": ok32, "median_ours": med, "median_stock_fp32": med32, "worst_stock_fp32": yard[0]})

@@ -29,6 +29,14 @@ def test_op_exact_ties_emulated(name, stride):
     P.op_vs_stock(name, 8, stride, True, 2, 12, "cpu", quantized=True)
 
 
+@pytest.mark.parametrize("cpb", ["2", "3"])
+def test_pointwise_backward_walks_several_chunks(cpb, monkeypatch):
+    """pw_bwd blocks that walk several 128-pixel chunks (what large batches use): 20 x 20 planes = 3 full chunks + a ragged one."""
+    monkeypatch.setenv("PCD_PW_CPB", cpb)
+    P.op_vs_stock("dil_conv_3x3", 8, 1, True, 2, 20, "cpu")
+    P.op_vs_stock("sep_conv_3x3", 16, 2, True, 1, 32, "cpu")
+
+
 def test_unsupported_ops_raise():
     from pcdarts.operations import OPS
     op = OPS["conv_7x1_1x7"](8, 1, True)
