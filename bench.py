@@ -477,7 +477,7 @@ def dp_parity(a, model, reducer, rank, world, dev, shard_batch=None, stepper=Non
             g_r = [torch.zeros_like(par[k]) if g is None else g for g, k in zip(g_r, keys)]
             acc = g_r if acc is None else [x + y for x, y in zip(acc, g_r)]
             if r == 0:
-                out["rank0_loss_rel_err"] = abs(float(loss) - float(l_r)) / abs(float(l_r))
+                out["rank0_loss_rel_err"] = abs(float(loss.detach()) - float(l_r.detach())) / abs(float(l_r.detach()))
         errs = []
         for k, g, ref in zip(keys, grads, acc):
             ref = ref / world

@@ -310,19 +310,33 @@ struct StemArgs {
 constexpr int kStemPx = 512;
 
 PCD_HOSTDEV size_t stem_smem_floats(int Cout) {
-    return (size_t)Cout * 27 + (size_t)16 * (Cout / 8) * (kStemPx / 4) + 16 * (Cout / 8) * 32 + 16;
+    return (size_t)Cout * 27 + (size_t)16 * (Cout / 8) * (kStemPx / 4) + 16 * (Cout / 8) * 32 + 16 + 3 * 1542;     // last term: max over W | 512 of (512 / W + 2) * (W + 2)
 }
 
+// (r2) the 3-channel input rows of the block's pixels (+ one halo row / column each side, zero outside the image) are staged in
+// shared memory when the block covers whole rows — every tap was a bounds-checked global load before (98 us per launch for
+// 50 MB of output) — and the outputs leave as float4.
 PCD_HD void stem_conv_body(const StemArgs& a, int bx, int n, float* smem) {
     const int Cout = a.Cout, HW = a.H * a.W, NCG = Cout / 8, NSTRIPMAX = kStemPx / 4;
     float* Wt = smem;
     float* P = Wt + Cout * 27;
     float* P2 = P + 16 * NCG * NSTRIPMAX;
+    float* XS = P2 + 16 * NCG * 32 + 16;         // [3][rows + 2][W + 2]
     PCD_FOR(i, Cout * 27) Wt[i] = a.w[i];
-    PCD_SYNC();
     const int p0 = bx * kStemPx;
     const int NT = NCG * NSTRIPMAX;
     const float* xb = a.x + (long long)n * 3 * HW;
+    // whole rows per block, strips inside one row, the tile fits the buffer sized for W >= 4
+    const bool tiled = (a.W % 4 == 0) && (kStemPx % a.W == 0) && (a.W <= kStemPx) && ((((uintptr_t)a.z) & 15) == 0);
+    const int rows = tiled ? kStemPx / a.W : 0, PW = a.W + 2, y0 = tiled ? p0 / a.W : 0;
+    if (tiled) {
+        PCD_FOR(i, 3 * (rows + 2) * PW) {
+            const int ci = i / ((rows + 2) * PW), r = (i - ci * (rows + 2) * PW) / PW, q = i - ci * (rows + 2) * PW - r * PW;
+            const int gy = y0 + r - 1, gx = q - 1;
+            XS[i] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? xb[(long long)ci * HW + gy * a.W + gx] : 0.f;
+        }
+    }
+    PCD_SYNC();
     PCD_FOR(task, NT) {
         const int cg = task / NSTRIPMAX, strip = task - cg * NSTRIPMAX;
         float acc[8][4];
@@ -331,31 +345,60 @@ PCD_HD void stem_conv_body(const StemArgs& a, int bx, int n, float* smem) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) acc[i][t] = 0.f;
         const int p = p0 + strip * 4;
-        for (int t = 0; t < 4; ++t) {
-            if (p + t >= HW) break;
-            const int oy = (p + t) / a.W, ox = (p + t) - oy * a.W;
-            for (int ci = 0; ci < 3; ++ci)
-                for (int ky = 0; ky < 3; ++ky)
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int gy = oy + ky - 1, gx = ox + kx - 1;
-                        if (gy < 0 || gy >= a.H || gx < 0 || gx >= a.W) continue;
-                        const float v = xb[(long long)ci * HW + gy * a.W + gx];
+        if (tiled) {
+            if (p < HW) {
+                const int oy = p / a.W, ox = p - oy * a.W;
+                for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            acc[i][t] = fmaf(Wt[(cg * 8 + i) * 27 + ci * 9 + ky * 3 + kx], v, acc[i][t]);
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const float* row = XS + (ci * (rows + 2) + (oy - y0) + ky) * PW + ox;      // image column ox - 1
+                        float v[6];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) v[j] = row[j];
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float w = Wt[(cg * 8 + i) * 27 + ci * 9 + ky * 3 + kx];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) acc[i][t] = fmaf(w, v[t + kx], acc[i][t]);
+                            }
                     }
+            }
+        } else {
+            for (int t = 0; t < 4; ++t) {
+                if (p + t >= HW) break;
+                const int oy = (p + t) / a.W, ox = (p + t) - oy * a.W;
+                for (int ci = 0; ci < 3; ++ci)
+                    for (int ky = 0; ky < 3; ++ky)
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int gy = oy + ky - 1, gx = ox + kx - 1;
+                            if (gy < 0 || gy >= a.H || gx < 0 || gx >= a.W) continue;
+                            const float v = xb[(long long)ci * HW + gy * a.W + gx];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                acc[i][t] = fmaf(Wt[(cg * 8 + i) * 27 + ci * 9 + ky * 3 + kx], v, acc[i][t]);
+                        }
+            }
         }
         float* zb = a.z + ((long long)n * Cout + cg * 8) * HW;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float s = 0.f, q = 0.f;
+            if (tiled && p < HW) {
+                F4 o = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+                *reinterpret_cast<F4*>(zb + (long long)i * HW + p) = o;
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-                if (p + t < HW) {
-                    zb[(long long)i * HW + p + t] = acc[i][t];
-                    s += acc[i][t];
-                    q = fmaf(acc[i][t], acc[i][t], q);
-                }
+                for (int t = 0; t < 4; ++t) { s += acc[i][t]; q = fmaf(acc[i][t], acc[i][t], q); }
+            } else if (!tiled) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (p + t < HW) {
+                        zb[(long long)i * HW + p + t] = acc[i][t];
+                        s += acc[i][t];
+                        q = fmaf(acc[i][t], acc[i][t], q);
+                    }
+            }
             P[(2 * i) * NT + task] = s;
             P[(2 * i + 1) * NT + task] = q;
         }
