@@ -252,6 +252,197 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 }
 
+// ---- persistent variant (r2) ------------------------------------------------------------------------------------------------
+// One CTA per SM walks the work list (output tile x K split); the accumulator is double-buffered in tensor memory (2 x BN
+// columns), so the epilogue of tile i (tcgen05.ld -> global stores, done by four DEDICATED warps) overlaps the TMA / split /
+// MMA pipeline of tile i + 1, which never drains between tiles.  Work order: m-tile fastest, so the CTAs running at one time
+// share a few B (weight) tiles through L2.
+//   warp 0 TMA | warp 1 MMA | warps 2-5 splitters | warps 6-9 epilogue (TMEM lane quadrant = warp % 4)
+//   full[s] -> split[s] -> MMA -> empty[s];   MMA -> accf[a] -> epilogue -> acce[a] -> MMA
+constexpr int kPersistThreads = 320;
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_tn_3xtf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+                              long long ldc, int M, int N, int K, const float* __restrict__ bias, int kb_per_split, int nsplit,
+                              int m_tiles, int n_tiles) {
+    using G = Cfg<BN, BK, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * G::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* split = bars + STAGES;
+    uint64_t* empty = bars + 2 * STAGES;
+    uint64_t* accf = bars + 3 * STAGES;          // [2]
+    uint64_t* acce = bars + 3 * STAGES + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_kb = (K + BK - 1) / BK;
+    const int nwork = m_tiles * n_tiles * nsplit;
+    const int atomic = nsplit > 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], kSplitThreads);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&accf[a], 1);
+            mbar_init(&acce[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto a_hi = [&](int s) { return smem + (size_t)s * G::STAGE_BYTES; };
+    auto b_hi = [&](int s) { return smem + (size_t)s * G::STAGE_BYTES + G::A_BYTES; };
+    auto a_lo = [&](int s) { return smem + (size_t)s * G::STAGE_BYTES + G::A_BYTES + G::B_BYTES; };
+    auto b_lo = [&](int s) { return smem + (size_t)s * G::STAGE_BYTES + 2 * G::A_BYTES + G::B_BYTES; };
+    // work item w -> (m tile fastest, n tile, split)
+    auto decode = [&](int w, int& m0, int& n0, int& kb0, int& nkb, int& z) {
+        const int mt = w % m_tiles, r = w / m_tiles, nt = r % n_tiles;
+        z = r / n_tiles;
+        m0 = mt * BM; n0 = nt * BN;
+        kb0 = z * kb_per_split;
+        const int kb1 = (kb0 + kb_per_split < total_kb) ? kb0 + kb_per_split : total_kb;
+        nkb = kb1 - kb0;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                int m0, n0, kb0, nkb, z;
+                decode(w, m0, n0, kb0, nkb, z);
+                for (int i = 0; i < nkb; ++i, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full[s], G::A_BYTES + G::B_BYTES);
+                    tma_load_2d(a_hi(s), &tmA, &full[s], (kb0 + i) * BK, m0);
+                    tma_load_2d(b_hi(s), &tmB, &full[s], (kb0 + i) * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t g = 0, it = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+                int m0, n0, kb0, nkb, z;
+                decode(w, m0, n0, kb0, nkb, z);
+                const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+                mbar_wait(&acce[as], aph ^ 1u);                       // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + as * (uint32_t)BN;
+                for (int i = 0; i < nkb; ++i, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1u;
+                    mbar_wait(&split[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t dah = umma_desc<G::ROWB>(smem_u32(a_hi(s))), dbh = umma_desc<G::ROWB>(smem_u32(b_hi(s)));
+                    const uint64_t dal = umma_desc<G::ROWB>(smem_u32(a_lo(s))), dbl = umma_desc<G::ROWB>(smem_u32(b_lo(s)));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+                        umma_tf32(tacc, dah + adv, dbh + adv, G::IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tacc, dah + adv, dbl + adv, G::IDESC, 1u);
+                        umma_tf32(tacc, dal + adv, dbh + adv, G::IDESC, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&accf[as]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---- splitters: lo = x - trunc13(x) of every landed stage, across tiles without a break ---------------------------
+        const int t = threadIdx.x - 64;
+        uint32_t g = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            int m0, n0, kb0, nkb, z;
+            decode(w, m0, n0, kb0, nkb, z);
+            for (int i = 0; i < nkb; ++i, ++g) {
+                const int s = g % STAGES;
+                const uint32_t ph = (g / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                const uint4* hi = reinterpret_cast<const uint4*>(a_hi(s));
+                uint4* lo = reinterpret_cast<uint4*>(a_lo(s));
+                constexpr int NV = (G::A_BYTES + G::B_BYTES) / 16 / kSplitThreads;
+#pragma unroll 8
+                for (int j = 0; j < NV; ++j) {
+                    const uint4 v = hi[t + kSplitThreads * j];
+                    uint4 l;
+                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+                    lo[t + kSplitThreads * j] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&split[s]);
+            }
+        }
+    } else {
+        // ---- epilogue warps 6..9: TMEM lane quadrant warp % 4 = rows m0 + 32 * (warp % 4) .. + 31 ---------------------------
+        const int q = warp & 3;
+        const bool vec_base = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+            int m0, n0, kb0, nkb, z;
+            decode(w, m0, n0, kb0, nkb, z);
+            const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+            mbar_wait(&accf[as], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+            float* crow = C + (long long)row * ldc;
+            const bool vec_ok = !atomic && vec_base;
+            const bool add_bias = bias != nullptr && z == 0;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + as * (uint32_t)BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                if (row < M) {
+                    const int col0 = n0 + c * 32;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const int col = col0 + 4 * j4;
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            v[j] = __uint_as_float(r[4 * j4 + j]);
+                            if (add_bias && col + j < N) v[j] += bias[col + j];
+                        }
+                        if (vec_ok && col + 3 < N) {
+                            *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (col + j < N) {
+                                    if (atomic) atomicAdd(crow + col + j, v[j]);
+                                    else crow[col + j] = v[j];
+                                }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acce[as]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -315,6 +506,52 @@ static int run(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long
     return PCD_OK;
 }
 
+static bool persist_enabled() {
+    static const bool on = !(getenv("PCD_GEMM_PERSIST") && getenv("PCD_GEMM_PERSIST")[0] == '0');
+    return on;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaDeviceProp p;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+        n = p.multiProcessorCount;
+    }
+    return n;
+}
+
+template <int BN, int BK, int STAGES>
+static int run_persist(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long ldc, int M, int N, int K, const float* bias,
+                       int split_k, cudaStream_t st) {
+    using G = Cfg<BN, BK, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tn_3xtf32_persist_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES) != cudaSuccess)
+            return PCD_ERR_CUDA;
+        configured = true;
+    }
+    const int total_kb = (K + BK - 1) / BK;
+    int kbps = (total_kb + split_k - 1) / split_k;
+    if (kbps < 1) kbps = 1;
+    const int nsplit = (total_kb + kbps - 1) / kbps;
+    const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+    const long long nwork = (long long)m_tiles * n_tiles * nsplit;
+    if (nwork > (1LL << 30)) return PCD_ERR_UNSUPPORTED;
+    const int grid = nwork < sm_count() ? (int)nwork : sm_count();
+    gemm_tn_3xtf32_persist_kernel<BN, BK, STAGES><<<grid, kPersistThreads, G::SMEM_BYTES, st>>>(ta, tb, C, ldc, M, N, K, bias, kbps, nsplit,
+                                                                                            m_tiles, n_tiles);
+    LaunchState& L = launch_state();
+    count_launch(L);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(L.last_err, sizeof L.last_err, "launch gemm_tn_3xtf32_persist: %s", cudaGetErrorString(e));
+        return PCD_ERR_CUDA;
+    }
+    return PCD_OK;
+}
+
 }  // namespace gemm
 }  // namespace pcd
 
@@ -335,6 +572,14 @@ extern "C" int pcd_gemm_tn_3xtf32(const float* A, long long lda, const float* B,
     if (split_k > total_kb) split_k = total_kb;
     if (split_k > 1) {      // partial sums are added atomically: start from zero
         if (cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st) != cudaSuccess) return PCD_ERR_CUDA;
+    }
+    if (gemm::persist_enabled()) {          // double-buffered accumulators need 2 * BN <= 512 tensor-memory columns: both tiles fit
+        switch (cfg) {
+            case 1: return gemm::run_persist<256, 32, 2>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
+            case 2: return gemm::run_persist<128, 32, 3>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
+            case 3: return gemm::run_persist<256, 16, 4>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
+            default: return gemm::run_persist<128, 16, 6>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
+        }
     }
     switch (cfg) {
         case 1: return gemm::run<256, 32, 2, false>(ta, tb, C, ldc, M, N, K, bias, split_k, st);
