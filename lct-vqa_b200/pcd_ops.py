@@ -166,6 +166,14 @@ def weight_grads_enabled():
     return _WEIGHT_GRADS[0]
 
 
+def _param_grads(ctx, *idx):
+    """Which PARAMETER gradients a dense Function's backward has to produce: needs_input_grad mirrors requires_grad, so inside
+    `weight_grads(False)` (the architect's passes that only differentiate w.r.t. alpha / beta) every weight / bias product —
+    two of the three GEMMs of a Linear, the LSTM's dW_ih / dW_hh — would be computed and thrown away."""
+    on = _WEIGHT_GRADS[0]
+    return tuple(bool(on and i is not None and ctx.needs_input_grad[i]) for i in idx)
+
+
 # ---- weight-grad overlap (pcd_set_overlap): buffers of a Cell backward stay alive until the join ----------------
 _OVERLAP = {"on": False, "keep": []}
 
@@ -573,6 +581,7 @@ class Linear3xTF32Function(torch.autograd.Function):
         m, k = x2.shape
         g2 = _f32c(gy.reshape(m, n))
         gx = gw = gb = None
+        need_w, need_b = _param_grads(ctx, 1, 2 if has_bias else None)
         if ctx.needs_input_grad[0]:
             if npad == n:
                 gp = g2
@@ -584,12 +593,12 @@ class Linear3xTF32Function(torch.autograd.Function):
             gx2 = _empty((m, k), torch.float32, x2.device)
             _gemm_tn(lib, gp, npad, wt, npad, gx2, k, m, k, npad, None, _auto_split(m, k, npad), x2)
             gx = gx2.view(xshape)
-        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+        if need_w or need_b:
             mp = _pad4(m)
             gt = _transpose_pad(lib, g2, n, m, n, mp, x2)           # (n, mp)
-            if has_bias and ctx.needs_input_grad[2]:
+            if need_b:
                 gb = gt.sum(1)
-            if ctx.needs_input_grad[1]:
+            if need_w:
                 xt = _transpose_pad(lib, x2, k, m, k, mp, x2)       # (k, mp)
                 gw = _empty((n, k), torch.float32, x2.device)
                 _gemm_tn(lib, gt, mp, xt, mp, gw, k, n, k, mp, None, _auto_split(n, k, mp), x2)
@@ -627,10 +636,11 @@ class SmallLinearFunction(torch.autograd.Function):
             gx2 = _empty((m, k), torch.float32, x2.device)
             N.check(lib, lib.pcd_gemm_small_f32(N.ptr(g2), n, 1, N.ptr(w), 1, k, N.ptr(gx2), k, m, k, n, None, st), "pcd_gemm_small_f32")
             gx = gx2.view(xshape)
-        if ctx.needs_input_grad[1]:         # dW[n][k] = sum_m dy[m][n] x[m][k]
+        need_w, need_b = _param_grads(ctx, 1, 2 if has_bias else None)
+        if need_w:                          # dW[n][k] = sum_m dy[m][n] x[m][k]
             gw = _empty((n, k), torch.float32, x2.device)
             N.check(lib, lib.pcd_gemm_small_f32(N.ptr(g2), 1, n, N.ptr(x2), 1, k, N.ptr(gw), k, n, k, m, None, st), "pcd_gemm_small_f32")
-        if has_bias and ctx.needs_input_grad[2]:
+        if need_b:
             gb = g2.sum(0)
         return gx, gw, gb
 
@@ -694,13 +704,13 @@ class VocabCrossEntropyFunction(torch.autograd.Function):
             gx2 = _empty((m, k), torch.float32, x2.device)
             _gemm_tn(lib, dl, vp, wt, vp, gx2, k, m, k, vp, None, max(_auto_split(m, k, vp), min(32, vp // 1024)), x2)
             gx = gx2.view(xshape)
-        need_b = has_bias and ctx.needs_input_grad[2]
-        if ctx.needs_input_grad[1] or need_b:
+        need_w, need_b = _param_grads(ctx, 1, 2 if has_bias else None)
+        if need_w or need_b:
             mp = _pad4(m)
             dlt = _transpose_pad(lib, dl, vp, m, v, mp, x2)                  # dlogits^T (v, mp)
             if need_b:
                 gb = dlt.sum(1)
-            if ctx.needs_input_grad[1]:
+            if need_w:
                 xt = _transpose_pad(lib, x2, k, m, k, mp, x2)                # h^T (k, mp)
                 gw = _empty((v, k), torch.float32, x2.device)
                 _gemm_tn(lib, dlt, mp, xt, mp, gw, k, v, k, mp, None, 1, x2)
@@ -769,24 +779,25 @@ class LstmFunction(torch.autograd.Function):
             gx_in = _empty((m, E), torch.float32, dev)
             _gemm_tn(lib, dg, 4 * H, wit, 4 * H, gx_in, E, m, E, 4 * H, None, _auto_split(m, E, 4 * H), xc)
             gx_in = gx_in.view(T, B, E)
-        if any(ctx.needs_input_grad[3:]):
+        need_wi, need_wh, need_bi, need_bh = _param_grads(ctx, 3, 4, 5, 6)
+        if need_wi or need_wh or need_bi or need_bh:
             mp = _pad4(m)
             dgt = _transpose_pad(lib, dg, 4 * H, m, 4 * H, mp, xc)             # dgates^T (4H, mp)
-            gb = dgt.sum(1) if (ctx.needs_input_grad[5] or ctx.needs_input_grad[6]) else None
-            if ctx.needs_input_grad[3]:
+            gb = dgt.sum(1) if (need_bi or need_bh) else None
+            if need_wi:
                 xt = _transpose_pad(lib, xc.view(m, E), E, m, E, mp, xc)       # x^T (E, mp)
                 gwi = _empty((4 * H, E), torch.float32, dev)
                 _gemm_tn(lib, dgt, mp, xt, mp, gwi, E, 4 * H, E, mp, None, _auto_split(4 * H, E, mp), xc)
-            if ctx.needs_input_grad[4]:
+            if need_wh:
                 hprev = torch.cat((h0c.unsqueeze(0), hs[:-1]), 0).view(m, H)   # h_{t-1} for every step
                 ht = _transpose_pad(lib, hprev, H, m, H, mp, xc)               # (H, mp)
                 gwh = _empty((4 * H, H), torch.float32, dev)
                 _gemm_tn(lib, dgt, mp, ht, mp, gwh, H, 4 * H, H, mp, None, _auto_split(4 * H, H, mp), xc)
         return (gx_in, dh0 if ctx.needs_input_grad[1] else None, dc0 if ctx.needs_input_grad[2] else None, gwi, gwh,
-                gb if ctx.needs_input_grad[5] else None,
+                gb if need_bi else None,
                 # b_ih and b_hh get the same values but must not share one buffer: in-place consumers (the data-parallel
                 # all-reduce, the flat clip scaling) would otherwise touch it twice — concurrently, in the clip kernel
-                (gb.clone() if ctx.needs_input_grad[5] else gb) if ctx.needs_input_grad[6] else None)
+                (gb.clone() if need_bi else gb) if need_bh else None)
 
 
 _LSTM_BATCH = 64        # rows one launch of the cooperative recurrence / decode kernels takes; larger batches are tiled

@@ -177,6 +177,32 @@ def test_lstm_bias_grads_do_not_share_a_buffer():
     assert torch.equal(g_ih, g_hh) and g_ih.data_ptr() != g_hh.data_ptr()
 
 
+def test_activation_only_passes_skip_parameter_products():
+    """Inside pcd_ops.weight_grads(False) (the architect's alpha-only passes, architect_vqa.py:110,115) the dense Functions
+    return the data gradients unchanged and no weight / bias gradient at all."""
+    import pcd_ops
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(8, 12)
+    lstm = torch.nn.LSTM(8, 32, 1)
+    x = torch.randn(5, 3, 8, requires_grad=True)
+    h0 = (0.3 * torch.randn(1, 3, 32)).requires_grad_(True)
+    tgt = torch.randint(0, 12, (15,))
+
+    def run():
+        out, _ = pcd_ops.lstm_forward(lstm, x, h0, h0)
+        proj = torch.nn.Linear(32, 8)
+        proj.load_state_dict({"weight": torch.ones(8, 32) / 32, "bias": torch.zeros(8)})
+        y = pcd_ops.linear_3xtf32(pcd_ops.linear_3xtf32(out, proj.weight, proj.bias), lin.weight, lin.bias)
+        loss = pcd_ops.vocab_cross_entropy(y.reshape(15, 12), torch.eye(12), None, tgt) + y.square().mean()
+        params = [lin.weight, lin.bias] + list(lstm.parameters())
+        return torch.autograd.grad(loss, [x, h0] + params, allow_unused=True)
+    full = run()
+    with pcd_ops.weight_grads(False):
+        act = run()
+    assert torch.equal(full[0], act[0]) and torch.equal(full[1], act[1])
+    assert all(g is not None for g in full[2:]) and all(g is None for g in act[2:])
+
+
 def test_make_capturable_moves_adam_step_counters():
     """search.make_capturable flips an optimizer that has already stepped (host-side `step` counters) to the capturable form."""
     from search import make_capturable
