@@ -545,10 +545,24 @@ def _stock(what):
                            "pcd_ops.allow_stock_ops(True) opts in to the stock torch op")
 
 
+_SMS = 148          # B200
+
+
 def _auto_split(m, n, k):
-    """Split K over blockIdx.z when the output has too few 128 x 256 tiles to fill 148 SMs (keeps >= 8 k-blocks per split)."""
-    tiles = ((m + 127) // 128) * ((n + 255) // 256)
-    return max(1, min(32, (k // 16) // 8, (148 + tiles - 1) // tiles))
+    """K split of pcd_gemm_tn_3xtf32 when the output has fewer tiles than SMs.  The persistent kernel deals its work items
+    (tile x split) round-robin to one CTA per SM, so the time is rounds x (k-blocks per item + pipeline fill): 30 tiles x 5 splits
+    = 150 items is TWO rounds on 148 SMs (the previous rule, ceil(148 / tiles)), 30 x 4 = 120 items one.  Fewest splits within
+    2 % of the best (each split adds one atomic pass over the output); >= 8 k-blocks per split; tiles as the kernel picks them
+    (128 x 256 x 16 for N >= 256, else 128 x 128 x 32)."""
+    bn, bk = (256, 16) if n >= 256 else (128, 32)
+    tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+    kb = (k + bk - 1) // bk
+    smax = max(1, min(32, kb // 8))
+    if tiles >= _SMS or smax == 1:
+        return 1
+    cost = {s: -(-tiles * s // _SMS) * (kb / s + 8.0) for s in range(1, smax + 1)}
+    best = min(cost.values())
+    return min(s for s, c in cost.items() if c <= 1.02 * best)
 
 
 class Linear3xTF32Function(torch.autograd.Function):
@@ -702,7 +716,7 @@ class VocabCrossEntropyFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = _transpose_pad(lib, w, k, v, k, vp, x2)                     # W^T (k, vp)
             gx2 = _empty((m, k), torch.float32, x2.device)
-            _gemm_tn(lib, dl, vp, wt, vp, gx2, k, m, k, vp, None, max(_auto_split(m, k, vp), min(32, vp // 1024)), x2)
+            _gemm_tn(lib, dl, vp, wt, vp, gx2, k, m, k, vp, None, _auto_split(m, k, vp), x2)
             gx = gx2.view(xshape)
         need_w, need_b = _param_grads(ctx, 1, 2 if has_bias else None)
         if need_w or need_b:

@@ -66,7 +66,10 @@ class QstEncoder(nn.Module):
     def forward(self, question, image_embedding, return_states=False):
         self.lstm.flatten_parameters()
         h0 = image_embedding.view(1, -1, self.hidden_size)
-        words = self.tanh(self.word2vec(question)).transpose(0, 1)          # T x B x E (teacher forcing)
+        # alpha-only passes (pcd_ops.weight_grads(False)): nothing behind the word embedding is differentiated, so the LSTM's
+        # input-gradient GEMM is not asked for either
+        with torch.set_grad_enabled(torch.is_grad_enabled() and pcd_ops.weight_grads_enabled()):
+            words = self.tanh(self.word2vec(question)).transpose(0, 1)          # T x B x E (teacher forcing)
         out, (hidden, cell) = lstm_forward(self.lstm, words, h0, h0)      # persistent recurrence kernels + tcgen05 GEMMs
         feat = torch.cat((hidden, cell), 2).transpose(0, 1)
         feat = linear_3xtf32(self.tanh(feat.reshape(feat.size(0), -1)), self.fc2.weight, self.fc2.bias)
