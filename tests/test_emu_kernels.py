@@ -166,7 +166,7 @@ def test_lstm_and_decode_tile_batches_above_64():
 def test_lstm_bias_grads_do_not_share_a_buffer():
     """b_ih and b_hh get equal gradients in SEPARATE tensors.  One shared buffer is touched twice by every in-place consumer:
     under data parallelism the flat clip kernel then scaled it from two thread blocks at once and 4 replicas drifted apart
-    (profiles/r02_bench_dp4_drift.json; scratch/dp_drift.py pinned it to these two parameters)."""
+    (profiles/r02_bench_dp4_drift.json; profiles/tools/dp_drift.py pinned it to these two parameters)."""
     import pcd_ops
     torch.manual_seed(2)
     lstm = torch.nn.LSTM(8, 32, 1)
