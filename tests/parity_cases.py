@@ -891,3 +891,31 @@ def derived_vs_stock(device, B=2, img=32, C=16, layers=4, tol=1e-4, share=0.97):
         else:
             assert_close(b1.double().cpu(), b2, 1e-4, k)
     return ok, (errs[:3], {"stock_fp32_share": ok32, "median_ours": med, "median_stock_fp32": med32, "worst_stock_fp32": yard[0]})
+
+
+def stem_vs_torch(device, B, H, W, C=16, tol=2e-5):
+    """Network.stem (Conv2d(3, 3C, 3, padding=1) + affine BatchNorm2d, model_search.py:110-113) through pcd_stem_* against the
+    same two layers in float64: forward, weight / gamma / beta gradients, running statistics.  W = 64 / 32 take the staged-tile
+    path (whole rows per block), other widths the generic one."""
+    import copy
+    import pcd_ops
+    torch.manual_seed(B + H + W)
+    stem = torch.nn.Sequential(torch.nn.Conv2d(3, 3 * C, 3, padding=1, bias=False), torch.nn.BatchNorm2d(3 * C)).train()
+    with torch.no_grad():
+        stem[1].weight.copy_(1.0 + 0.3 * torch.randn(3 * C))
+        stem[1].bias.copy_(0.3 * torch.randn(3 * C))
+    ref = copy.deepcopy(stem).double()
+    stem = stem.to(device)
+    ar = pcd_ops.Arena(stem).ensure()
+    x = torch.randn(B, 3, H, W)
+    y = pcd_ops.StemFunction.apply(x.to(device), (ar.param_ptr, ar.running_ptr, ar.nbt_ptr), *ar.params)
+    yr = ref(x.double())
+    gy = torch.randn(yr.shape)
+    got = torch.autograd.grad(y, list(stem.parameters()), gy.to(device))
+    exp = torch.autograd.grad(yr, list(ref.parameters()), gy.double())
+    assert_close(y.double().cpu(), yr, tol, "stem forward")
+    for a_, b_, (n, _) in zip(got, exp, stem.named_parameters()):
+        assert_close(a_.double().cpu(), b_, tol, f"stem {n}")
+    assert_close(stem[1].running_mean.double().cpu(), ref[1].running_mean, 1e-5, "running_mean")
+    assert_close(stem[1].running_var.double().cpu(), ref[1].running_var, 1e-5, "running_var")
+    assert int(stem[1].num_batches_tracked) == 1

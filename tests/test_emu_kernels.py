@@ -203,6 +203,11 @@ def test_activation_only_passes_skip_parameter_products():
     assert all(g is not None for g in full[2:]) and all(g is None for g in act[2:])
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 16, 32), (2, 10, 20), (1, 9, 9), (2, 8, 128)])
+def test_stem_vs_torch_emulated(B, H, W):
+    P.stem_vs_torch("cpu", B, H, W)
+
+
 def test_make_capturable_moves_adam_step_counters():
     """search.make_capturable flips an optimizer that has already stepped (host-side `step` counters) to the capturable form."""
     from search import make_capturable

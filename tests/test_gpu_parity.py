@@ -399,3 +399,8 @@ def test_derived_network_vs_stock(B, img):
     """The network a genotype describes (pcdarts/model.py): stem, 4 derived cells, pooling; forward + every weight gradient."""
     ok, worst = P.derived_vs_stock(DEV, B=B, img=img)
     print(f"derived network B={B} img={img}: share within 1e-4 = {ok:.3f}, worst {worst}")
+
+
+@pytest.mark.parametrize("B,H,W", [(64, 64, 64), (5, 32, 32), (2, 10, 20), (1, 9, 9)])
+def test_stem_vs_torch(B, H, W):
+    P.stem_vs_torch(DEV, B, H, W)
