@@ -428,7 +428,16 @@ def dp_parity(a, model, reducer, rank, world, dev, shard_batch=None, stepper=Non
     # OpenMP threads oversubscribed, an 8-rank run took > 8 minutes here
     if shard_batch is None:
         shard_batch = max(2, 16 // world)
-    cpu_group = dist.new_group(backend="gloo")
+    cpu_group = None
+    try:
+        import datetime
+        cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=120))
+        ok = torch.ones(1, device=dev)
+    except Exception:
+        ok = torch.zeros(1, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok) < 1.0:      # some rank has no gloo group: everybody falls back to the (spinning) NCCL barrier
+        cpu_group = None
     with torch.no_grad():
         tensors = [p.detach() for p in model.parameters()] + [t.detach() for t in model.arch_parameters()]
         arch = [t.detach() for t in model.arch_parameters()]
@@ -488,7 +497,7 @@ def dp_parity(a, model, reducer, rank, world, dev, shard_batch=None, stepper=Non
             "tensors": len(errs), "share_within_1e-4": sum(e <= 1e-4 for e, _ in errs) / len(errs), "worst": errs[:3],
             "shards": world, "samples_per_shard": shard_batch, "oracle_seconds": round(time.time() - t_oracle, 1),
             "note": "search-net tensors beyond 1e-4 are ReLU / max-pool tie flips (~1/sqrt(B*H*W), DESIGN.md §2)"}
-    dist.barrier(group=cpu_group)
+    dist.barrier(group=cpu_group) if cpu_group is not None else dist.barrier()
     return out
 
 
